@@ -1,0 +1,66 @@
+"""ctypes binding of libhspose_b200.so (the C ABI in include/hspose_b200.h)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libhspose_b200.so")
+
+c_int, c_void_p, c_size_t = ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t
+P = c_void_p
+
+# name -> (restype, argtypes); must list every symbol the header declares.
+SIGNATURES = {
+    "hsp_version": (c_int, []),
+    "hsp_strerror": (ctypes.c_char_p, [c_int]),
+    "hsp_device_check": (c_int, []),
+    "hsp_knn3": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "hsp_knn_feat_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "hsp_knn_feat": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_size_t, P]),
+    "hsp_neighbor_direction_norm": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
+    "hsp_surface_conv_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "hsp_surface_conv_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
+    "hsp_surface_conv_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P,
+                                     c_size_t, P]),
+    "hsp_graph_conv_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "hsp_graph_conv_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
+    "hsp_graph_conv_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P,
+                                   P, c_size_t, P]),
+    "hsp_gather_max_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "hsp_gather_max_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "hsp_orl_global_workspace_bytes": (c_size_t, [c_int] * 3),
+    "hsp_orl_global_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P, c_size_t, P]),
+    "hsp_orl_global_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P]),
+    "hsp_upsample_rows_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P, c_int, c_int, P]),
+    "hsp_upsample_rows_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "hsp_chamfer_fwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P, P]),
+    "hsp_chamfer_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, P]),
+}
+
+_lib = None
+
+
+class HSPoseLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Fails loudly — there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HSPoseLibraryError(
+            f"{LIB_PATH} not found: build it with `make` (or __graft_entry__.build()); "
+            "hs-pose_b200 has no CPU / PyTorch fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().hsp_strerror(code).decode()
+        raise HSPoseLibraryError(f"{what} failed: {msg} ({code})")

@@ -1,0 +1,228 @@
+// K5 — row gathers fused with their reductions (forward + backward).
+//   hsp_gather_max_*     Pool_layer.forward (reference gcn3d.py:234-246)
+//   hsp_orl_global_*     get_ORL_global     (gcn3d.py:211-218)
+//   hsp_upsample_rows_*  nearest up-sampling (FaceRecon.py:100-104)
+// indexing_neighbor_new (gcn3d.py:39-47) never materialises (B,N,k,C): one
+// thread owns one channel, a warp reads 128 contiguous bytes of each gathered
+// row, the max over neighbours stays in a register.
+#include "common.cuh"
+
+namespace hsp {
+
+constexpr int GO_THREADS = 128;
+constexpr int GO_PT = 8;  // rows per CTA
+
+__global__ void __launch_bounds__(GO_THREADS)
+gather_max_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx,
+                      const int32_t* __restrict__ rows, int N, int C, int R, int kuse,
+                      int kstride, float* __restrict__ out, uint8_t* __restrict__ argmax) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.z * GO_THREADS + threadIdx.x;
+  if (c >= C) return;
+  const float* fb = feat + (size_t)b * N * C;
+  const int r_end = min((int)(blockIdx.x + 1) * GO_PT, R);
+  for (int r = blockIdx.x * GO_PT; r < r_end; ++r) {
+    const int i = rows ? __ldg(rows + r) : r;
+    const int32_t* ip = idx + ((size_t)b * N + i) * kstride;
+    float m = -INFINITY;
+    int am = 0;
+    for (int n = 0; n < kuse; ++n) {
+      float v = __ldg(fb + (size_t)__ldg(ip + n) * C + c);
+      if (v > m) { m = v; am = n; }
+    }
+    out[((size_t)b * R + r) * C + c] = m;
+    if (argmax) argmax[((size_t)b * R + r) * C + c] = (uint8_t)am;
+  }
+}
+
+__global__ void __launch_bounds__(GO_THREADS)
+gather_max_bwd_kernel(const float* __restrict__ gout, const int32_t* __restrict__ idx,
+                      const int32_t* __restrict__ rows, const uint8_t* __restrict__ argmax,
+                      int N, int C, int R, int kstride, float* __restrict__ gfeat) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.z * GO_THREADS + threadIdx.x;
+  if (c >= C) return;
+  const int r_end = min((int)(blockIdx.x + 1) * GO_PT, R);
+  for (int r = blockIdx.x * GO_PT; r < r_end; ++r) {
+    const int i = rows ? __ldg(rows + r) : r;
+    const size_t o = ((size_t)b * R + r) * C + c;
+    const int src = __ldg(idx + ((size_t)b * N + i) * kstride + argmax[o]);
+    atomicAdd(gfeat + ((size_t)b * N + src) * C + c, gout[o]);
+  }
+}
+
+// Stage 1 of ORL: per-tile partial sums over points of max over neighbours.
+__global__ void __launch_bounds__(GO_THREADS)
+orl_partial_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx, int N, int C,
+                   int k, int tile, float* __restrict__ partial, uint8_t* __restrict__ argmax) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.z * GO_THREADS + threadIdx.x;
+  if (c >= C) return;
+  const float* fb = feat + (size_t)b * N * C;
+  const int i_end = min((int)(blockIdx.x + 1) * tile, N);
+  float sum = 0.0f;
+  for (int i = blockIdx.x * tile; i < i_end; ++i) {
+    const int32_t* ip = idx + ((size_t)b * N + i) * k;
+    float m = -INFINITY;
+    int am = 0;
+    for (int n = 0; n < k; ++n) {
+      float v = __ldg(fb + (size_t)__ldg(ip + n) * C + c);
+      if (v > m) { m = v; am = n; }
+    }
+    sum += m;
+    if (argmax) argmax[((size_t)b * N + i) * C + c] = (uint8_t)am;
+  }
+  partial[((size_t)b * gridDim.x + blockIdx.x) * C + c] = sum;
+}
+// Stage 2: fixed-order sum of the tile partials (deterministic), mean over N.
+__global__ void orl_finish_kernel(const float* __restrict__ partial, int tiles, int C, int N,
+                                  float* __restrict__ G) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int t = 0; t < tiles; ++t) s += (double)partial[((size_t)b * tiles + t) * C + c];
+  G[(size_t)b * C + c] = (float)(s / (double)N);
+}
+
+__global__ void __launch_bounds__(GO_THREADS)
+orl_bwd_kernel(const float* __restrict__ gG, const int32_t* __restrict__ idx,
+               const uint8_t* __restrict__ argmax, int N, int C, int k,
+               float* __restrict__ gfeat) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.z * GO_THREADS + threadIdx.x;
+  if (c >= C) return;
+  const float g = gG[(size_t)b * C + c] / (float)N;
+  const int i_end = min((int)(blockIdx.x + 1) * GO_PT, N);
+  for (int i = blockIdx.x * GO_PT; i < i_end; ++i) {
+    const int src = __ldg(idx + ((size_t)b * N + i) * k + argmax[((size_t)b * N + i) * C + c]);
+    atomicAdd(gfeat + ((size_t)b * N + src) * C + c, g);
+  }
+}
+
+__global__ void __launch_bounds__(GO_THREADS)
+upsample_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ nn, int Nsrc,
+                    int M, int C, float* __restrict__ out, int ldo, int col0) {
+  const int b = blockIdx.y;
+  const int i_end = min((int)(blockIdx.x + 1) * GO_PT, M);
+  for (int i = blockIdx.x * GO_PT; i < i_end; ++i) {
+    const float* src = feat + ((size_t)b * Nsrc + __ldg(nn + (size_t)b * M + i)) * C;
+    float* dst = out + ((size_t)b * M + i) * ldo + col0;
+    for (int c = threadIdx.x; c < C; c += GO_THREADS) dst[c] = __ldg(src + c);
+  }
+}
+__global__ void __launch_bounds__(GO_THREADS)
+upsample_bwd_kernel(const float* __restrict__ gout, const int32_t* __restrict__ nn, int Nsrc,
+                    int M, int C, int ldo, int col0, float* __restrict__ gfeat) {
+  const int b = blockIdx.y;
+  const int i_end = min((int)(blockIdx.x + 1) * GO_PT, M);
+  for (int i = blockIdx.x * GO_PT; i < i_end; ++i) {
+    float* dst = gfeat + ((size_t)b * Nsrc + __ldg(nn + (size_t)b * M + i)) * C;
+    const float* src = gout + ((size_t)b * M + i) * ldo + col0;
+    for (int c = threadIdx.x; c < C; c += GO_THREADS) atomicAdd(dst + c, src[c]);
+  }
+}
+
+static int orl_tile(int N) { return 16; }
+
+}  // namespace hsp
+
+extern "C" int hsp_gather_max_fwd(const float* feat, const int32_t* idx, const int32_t* rows,
+                                  int B, int N, int C, int R, int kuse, int kstride,
+                                  float* out, uint8_t* argmax, void* stream) {
+  using namespace hsp;
+  if (!feat || !idx || !out || B < 0 || N <= 0 || C <= 0 || R < 0 || kuse <= 0 ||
+      kuse > kstride || kuse > 255 || B > 65535 || (!rows && R != N))
+    return HSP_EINVAL;
+  if (B == 0 || R == 0) return HSP_OK;
+  dim3 grid((R + GO_PT - 1) / GO_PT, B, (C + GO_THREADS - 1) / GO_THREADS);
+  gather_max_fwd_kernel<<<grid, GO_THREADS, 0, (cudaStream_t)stream>>>(
+      feat, idx, rows, N, C, R, kuse, kstride, out, argmax);
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}
+
+extern "C" int hsp_gather_max_bwd(const float* gout, const int32_t* idx, const int32_t* rows,
+                                  const uint8_t* argmax, int B, int N, int C, int R, int kuse,
+                                  int kstride, float* gfeat, void* stream) {
+  using namespace hsp;
+  if (!gout || !idx || !argmax || !gfeat || B < 0 || N <= 0 || C <= 0 || R < 0 || kuse <= 0 ||
+      kuse > kstride || B > 65535 || (!rows && R != N))
+    return HSP_EINVAL;
+  if (B == 0 || R == 0) return HSP_OK;
+  dim3 grid((R + GO_PT - 1) / GO_PT, B, (C + GO_THREADS - 1) / GO_THREADS);
+  gather_max_bwd_kernel<<<grid, GO_THREADS, 0, (cudaStream_t)stream>>>(
+      gout, idx, rows, argmax, N, C, R, kstride, gfeat);
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}
+
+extern "C" size_t hsp_orl_global_workspace_bytes(int B, int N, int C) {
+  using namespace hsp;
+  if (B <= 0 || N <= 0 || C <= 0) return 0;
+  int tile = orl_tile(N);
+  return (size_t)B * ((N + tile - 1) / tile) * C * sizeof(float);
+}
+
+extern "C" int hsp_orl_global_fwd(const float* feat, const int32_t* idx, int B, int N, int C,
+                                  int k, float* G, uint8_t* argmax, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  using namespace hsp;
+  if (!feat || !idx || !G || B < 0 || N <= 0 || C <= 0 || k <= 0 || k > 255 || B > 65535)
+    return HSP_EINVAL;
+  if (B == 0) return HSP_OK;
+  if (!workspace || workspace_bytes < hsp_orl_global_workspace_bytes(B, N, C))
+    return HSP_EWORKSPACE;
+  const int tile = orl_tile(N), tiles = (N + tile - 1) / tile;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(tiles, B, (C + GO_THREADS - 1) / GO_THREADS);
+  orl_partial_kernel<<<grid, GO_THREADS, 0, st>>>(feat, idx, N, C, k, tile, (float*)workspace,
+                                                  argmax);
+  HSP_LAUNCH_CHECK();
+  dim3 grid2((C + 127) / 128, B);
+  orl_finish_kernel<<<grid2, 128, 0, st>>>((const float*)workspace, tiles, C, N, G);
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}
+
+extern "C" int hsp_orl_global_bwd(const float* gG, const int32_t* idx, const uint8_t* argmax,
+                                  int B, int N, int C, int k, float* gfeat, void* stream) {
+  using namespace hsp;
+  if (!gG || !idx || !argmax || !gfeat || B < 0 || N <= 0 || C <= 0 || k <= 0 || B > 65535)
+    return HSP_EINVAL;
+  if (B == 0) return HSP_OK;
+  dim3 grid((N + GO_PT - 1) / GO_PT, B, (C + GO_THREADS - 1) / GO_THREADS);
+  orl_bwd_kernel<<<grid, GO_THREADS, 0, (cudaStream_t)stream>>>(gG, idx, argmax, N, C, k, gfeat);
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}
+
+extern "C" int hsp_upsample_rows_fwd(const float* feat, const int32_t* nn, int B, int Nsrc,
+                                     int M, int C, float* out, int ldo, int col0,
+                                     void* stream) {
+  using namespace hsp;
+  if (!feat || !nn || !out || B < 0 || Nsrc <= 0 || M < 0 || C <= 0 || col0 < 0 ||
+      col0 + C > ldo || B > 65535)
+    return HSP_EINVAL;
+  if (B == 0 || M == 0) return HSP_OK;
+  dim3 grid((M + GO_PT - 1) / GO_PT, B);
+  upsample_fwd_kernel<<<grid, GO_THREADS, 0, (cudaStream_t)stream>>>(feat, nn, Nsrc, M, C, out,
+                                                                     ldo, col0);
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}
+
+extern "C" int hsp_upsample_rows_bwd(const float* gout, const int32_t* nn, int B, int Nsrc,
+                                     int M, int C, int ldo, int col0, float* gfeat,
+                                     void* stream) {
+  using namespace hsp;
+  if (!gout || !nn || !gfeat || B < 0 || Nsrc <= 0 || M < 0 || C <= 0 || col0 < 0 ||
+      col0 + C > ldo || B > 65535)
+    return HSP_EINVAL;
+  if (B == 0 || M == 0) return HSP_OK;
+  dim3 grid((M + GO_PT - 1) / GO_PT, B);
+  upsample_bwd_kernel<<<grid, GO_THREADS, 0, (cudaStream_t)stream>>>(gout, nn, Nsrc, M, C, ldo,
+                                                                     col0, gfeat);
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}

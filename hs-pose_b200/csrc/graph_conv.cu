@@ -1,0 +1,442 @@
+// K3 / K4 — fused receptive-field gather + direction kernel + max over
+// neighbours + mean over supports (+ centre term), forward and backward.
+//
+// Replaces HSlayer_surface.graph_conv (reference gcn3d.py:92-107) and
+// HS_layer.graph_conv (gcn3d.py:158-181) together with the gathers they call
+// (indexing_neighbor_new gcn3d.py:39-47, get_neighbor_direction_norm :49-59).
+// The (B,N,k,S*C) tensors theta / gathered support / product of the reference
+// are never written: one thread owns one output channel c of one point, keeps
+// the S column-normalised support directions of that channel in registers
+// (3*S floats) and the S running maxima in registers, and streams the k
+// neighbour rows of the support matrix P[..., C:] straight from L2 (each warp
+// reads 128 contiguous bytes per (neighbour, support)).  Unit directions of
+// the tile's (point, neighbour) pairs are computed once per CTA into shared
+// memory and broadcast.
+#include "common.cuh"
+
+namespace hsp {
+
+constexpr int GC_THREADS = 128;  // channels per CTA slice
+constexpr int GC_PT = 8;         // points per CTA tile
+constexpr int GC_MAXK = 64;
+
+// F.normalize(nbr - centre, dim=-1): x / max(||x||_2, 1e-12)   (gcn3d.py:53-55)
+__device__ __forceinline__ void unit_dir(const float* __restrict__ xb, int i, int j, float* r) {
+  float rx = __fsub_rn(xb[3 * j], xb[3 * i]);
+  float ry = __fsub_rn(xb[3 * j + 1], xb[3 * i + 1]);
+  float rz = __fsub_rn(xb[3 * j + 2], xb[3 * i + 2]);
+  float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz)));
+  float den = fmaxf(nrm, 1e-12f);
+  r[0] = __fdiv_rn(rx, den);
+  r[1] = __fdiv_rn(ry, den);
+  r[2] = __fdiv_rn(rz, den);
+}
+
+// Stage idx and unit directions of a tile of points into shared memory.
+__device__ __forceinline__ void stage_tile(const float* __restrict__ xb,
+                                           const int32_t* __restrict__ idx_b, int i0, int npts,
+                                           int k, int* s_idx, float* s_r) {
+  for (int p = threadIdx.x; p < npts * k; p += blockDim.x) {
+    int i = i0 + p / k;
+    int nb = idx_b[(size_t)i * k + (p % k)];
+    s_idx[p] = nb;
+    float r[3];
+    unit_dir(xb, i, nb, r);
+    s_r[3 * p] = r[0];
+    s_r[3 * p + 1] = r[1];
+    s_r[3 * p + 2] = r[2];
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(GC_THREADS)
+surface_conv_fwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
+                        const float* __restrict__ dirn, int N, int k, int C,
+                        float* __restrict__ out) {
+  __shared__ int s_idx[GC_PT * GC_MAXK];
+  __shared__ float s_r[GC_PT * GC_MAXK * 3];
+  const int b = blockIdx.y, i0 = blockIdx.x * GC_PT;
+  const int npts = min(GC_PT, N - i0);
+  const int c = blockIdx.z * GC_THREADS + threadIdx.x;
+  const int SC = S * C;
+  stage_tile(xyz + (size_t)b * N * 3, idx + (size_t)b * N * k, i0, npts, k, s_idx, s_r);
+  float dx[S], dy[S], dz[S];
+  if (c < C) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      dx[s] = dirn[s * C + c];
+      dy[s] = dirn[SC + s * C + c];
+      dz[s] = dirn[2 * SC + s * C + c];
+    }
+  }
+  __syncthreads();
+  if (c >= C) return;
+  for (int p = 0; p < npts; ++p) {
+    float acc[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) acc[s] = 0.0f;  // max_n relu(x_n) = max(0, max_n x_n)
+    for (int n = 0; n < k; ++n) {
+      const float rx = s_r[3 * (p * k + n)], ry = s_r[3 * (p * k + n) + 1],
+                  rz = s_r[3 * (p * k + n) + 2];
+#pragma unroll
+      for (int s = 0; s < S; ++s)
+        acc[s] = fmaxf(acc[s], fmaf(rz, dz[s], fmaf(ry, dy[s], rx * dx[s])));
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int s = 0; s < S; ++s) sum += acc[s];
+    out[((size_t)b * N + i0 + p) * C + c] = __fdiv_rn(sum, (float)S);
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(GC_THREADS)
+graph_conv_fwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
+                      const float* __restrict__ dirn, const float* __restrict__ P, int N, int k,
+                      int C, float* __restrict__ out, uint8_t* __restrict__ argmax) {
+  __shared__ int s_idx[GC_PT * GC_MAXK];
+  __shared__ float s_r[GC_PT * GC_MAXK * 3];
+  const int b = blockIdx.y, i0 = blockIdx.x * GC_PT;
+  const int npts = min(GC_PT, N - i0);
+  const int c = blockIdx.z * GC_THREADS + threadIdx.x;
+  const int SC = S * C, LD = (S + 1) * C;
+  stage_tile(xyz + (size_t)b * N * 3, idx + (size_t)b * N * k, i0, npts, k, s_idx, s_r);
+  float dx[S], dy[S], dz[S];
+  if (c < C) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      dx[s] = dirn[s * C + c];
+      dy[s] = dirn[SC + s * C + c];
+      dz[s] = dirn[2 * SC + s * C + c];
+    }
+  }
+  __syncthreads();
+  if (c >= C) return;
+  const float* Pb = P + (size_t)b * N * LD;
+  for (int p = 0; p < npts; ++p) {
+    float acc[S];
+    int am[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { acc[s] = -INFINITY; am[s] = 0; }
+#pragma unroll 2
+    for (int n = 0; n < k; ++n) {
+      const float* sup = Pb + (size_t)s_idx[p * k + n] * LD + C + c;
+      float v[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) v[s] = __ldg(sup + s * C);
+      const float rx = s_r[3 * (p * k + n)], ry = s_r[3 * (p * k + n) + 1],
+                  rz = s_r[3 * (p * k + n) + 2];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float th = fmaxf(fmaf(rz, dz[s], fmaf(ry, dy[s], rx * dx[s])), 0.0f);
+        float a = th * v[s];
+        if (a > acc[s]) { acc[s] = a; am[s] = n; }
+      }
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int s = 0; s < S; ++s) sum += acc[s];
+    const size_t row = (size_t)b * N + i0 + p;
+    out[row * C + c] = Pb[(size_t)(i0 + p) * LD + c] + __fdiv_rn(sum, (float)S);
+    if (argmax) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) argmax[row * SC + s * C + c] = (uint8_t)am[s];
+    }
+  }
+}
+
+
+
+// get_neighbor_direction_norm (gcn3d.py:49-59) as a stand-alone op (API parity;
+// the fused kernels above never materialise it).
+__global__ void direction_norm_kernel(const float* __restrict__ xyz,
+                                      const int32_t* __restrict__ idx, int N, int k, int total,
+                                      float* __restrict__ out_norm, float* __restrict__ out_raw) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int bi = t / k, b = bi / N, i = bi % N;
+  const float* xb = xyz + (size_t)b * N * 3;
+  const int j = idx[t];
+  float r[3];
+  unit_dir(xb, i, j, r);
+  out_norm[3 * (size_t)t] = r[0];
+  out_norm[3 * (size_t)t + 1] = r[1];
+  out_norm[3 * (size_t)t + 2] = r[2];
+  if (out_raw) {
+    out_raw[3 * (size_t)t] = __fsub_rn(xb[3 * j], xb[3 * i]);
+    out_raw[3 * (size_t)t + 1] = __fsub_rn(xb[3 * j + 1], xb[3 * i + 1]);
+    out_raw[3 * (size_t)t + 2] = __fsub_rn(xb[3 * j + 2], xb[3 * i + 2]);
+  }
+}
+
+// ---------------------------------------------------------------- backward
+// Persistent CTAs walk (object, tile) work items; every thread keeps the
+// gradient of its channel's S support directions in registers, so the only
+// cross-CTA reduction is one fixed-order pass over gridDim.x partial rows
+// (deterministic, no float atomics on gdirn).
+constexpr int GC_BWD_CTAS = 148 * 4;
+
+template <int S>
+__global__ void __launch_bounds__(GC_THREADS)
+surface_conv_bwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
+                        const float* __restrict__ dirn, const float* __restrict__ gout, int B,
+                        int N, int k, int C, float* __restrict__ partial) {
+  __shared__ int s_idx[GC_PT * GC_MAXK];
+  __shared__ float s_r[GC_PT * GC_MAXK * 3];
+  const int c = blockIdx.z * GC_THREADS + threadIdx.x;
+  const int SC = S * C;
+  const int tiles = (N + GC_PT - 1) / GC_PT;
+  float dx[S], dy[S], dz[S], gx[S], gy[S], gz[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    gx[s] = gy[s] = gz[s] = 0.0f;
+    dx[s] = dy[s] = dz[s] = 0.0f;
+    if (c < C) {
+      dx[s] = dirn[s * C + c];
+      dy[s] = dirn[SC + s * C + c];
+      dz[s] = dirn[2 * SC + s * C + c];
+    }
+  }
+  for (int w = blockIdx.x; w < B * tiles; w += gridDim.x) {
+    const int b = w / tiles, i0 = (w % tiles) * GC_PT;
+    const int npts = min(GC_PT, N - i0);
+    __syncthreads();
+    stage_tile(xyz + (size_t)b * N * 3, idx + (size_t)b * N * k, i0, npts, k, s_idx, s_r);
+    __syncthreads();
+    if (c < C) {
+      for (int p = 0; p < npts; ++p) {
+        float acc[S];
+        int am[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) { acc[s] = 0.0f; am[s] = -1; }
+        for (int n = 0; n < k; ++n) {
+          const float rx = s_r[3 * (p * k + n)], ry = s_r[3 * (p * k + n) + 1],
+                      rz = s_r[3 * (p * k + n) + 2];
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            float th = fmaf(rz, dz[s], fmaf(ry, dy[s], rx * dx[s]));
+            if (th > acc[s]) { acc[s] = th; am[s] = n; }
+          }
+        }
+        const float gs = __fdiv_rn(gout[((size_t)b * N + i0 + p) * C + c], (float)S);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          if (am[s] >= 0) {
+            const float* r = s_r + 3 * (p * k + am[s]);
+            gx[s] = fmaf(gs, r[0], gx[s]);
+            gy[s] = fmaf(gs, r[1], gy[s]);
+            gz[s] = fmaf(gs, r[2], gz[s]);
+          }
+        }
+      }
+    }
+  }
+  if (c < C) {
+    float* pr = partial + (size_t)blockIdx.x * 3 * SC;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      pr[s * C + c] = gx[s];
+      pr[SC + s * C + c] = gy[s];
+      pr[2 * SC + s * C + c] = gz[s];
+    }
+  }
+}
+
+__global__ void dir_reduce_kernel(const float* __restrict__ partial, int rows, int cols,
+                                  float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  float s = 0.0f;
+  for (int r = 0; r < rows; ++r) s += partial[(size_t)r * cols + j];
+  out[j] = s;
+}
+
+template <int S>
+__global__ void __launch_bounds__(GC_THREADS)
+graph_conv_bwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
+                      const float* __restrict__ dirn, const float* __restrict__ P,
+                      const uint8_t* __restrict__ argmax, const float* __restrict__ gout, int B,
+                      int N, int k, int C, float* __restrict__ gP, float* __restrict__ partial) {
+  __shared__ int s_idx[GC_PT * GC_MAXK];
+  __shared__ float s_r[GC_PT * GC_MAXK * 3];
+  const int c = blockIdx.z * GC_THREADS + threadIdx.x;
+  const int SC = S * C, LD = (S + 1) * C;
+  const int tiles = (N + GC_PT - 1) / GC_PT;
+  float dx[S], dy[S], dz[S], gx[S], gy[S], gz[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    gx[s] = gy[s] = gz[s] = 0.0f;
+    dx[s] = dy[s] = dz[s] = 0.0f;
+    if (c < C) {
+      dx[s] = dirn[s * C + c];
+      dy[s] = dirn[SC + s * C + c];
+      dz[s] = dirn[2 * SC + s * C + c];
+    }
+  }
+  for (int w = blockIdx.x; w < B * tiles; w += gridDim.x) {
+    const int b = w / tiles, i0 = (w % tiles) * GC_PT;
+    const int npts = min(GC_PT, N - i0);
+    __syncthreads();
+    stage_tile(xyz + (size_t)b * N * 3, idx + (size_t)b * N * k, i0, npts, k, s_idx, s_r);
+    __syncthreads();
+    if (c < C) {
+      const float* Pb = P + (size_t)b * N * LD;
+      float* gPb = gP + (size_t)b * N * LD;
+      for (int p = 0; p < npts; ++p) {
+        const size_t row = (size_t)b * N + i0 + p;
+        const float g = gout[row * C + c];
+        gPb[(size_t)(i0 + p) * LD + c] = g;  // centre term
+        const float gs = __fdiv_rn(g, (float)S);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int n = argmax[row * SC + s * C + c];
+          const float* r = s_r + 3 * (p * k + n);
+          const size_t off = (size_t)s_idx[p * k + n] * LD + C + s * C + c;
+          const float th = fmaxf(fmaf(r[2], dz[s], fmaf(r[1], dy[s], r[0] * dx[s])), 0.0f);
+          if (th > 0.0f) {
+            atomicAdd(gPb + off, gs * th);
+            const float gv = gs * __ldg(Pb + off);
+            gx[s] = fmaf(gv, r[0], gx[s]);
+            gy[s] = fmaf(gv, r[1], gy[s]);
+            gz[s] = fmaf(gv, r[2], gz[s]);
+          }
+        }
+      }
+    }
+  }
+  if (c < C) {
+    float* pr = partial + (size_t)blockIdx.x * 3 * SC;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      pr[s * C + c] = gx[s];
+      pr[SC + s * C + c] = gy[s];
+      pr[2 * SC + s * C + c] = gz[s];
+    }
+  }
+}
+
+static int bwd_ctas(int B, int N) {
+  long items = (long)B * ((N + GC_PT - 1) / GC_PT);
+  return (int)(items < GC_BWD_CTAS ? items : GC_BWD_CTAS);
+}
+
+#define HSP_DISPATCH_S(S_, CALL)                 \
+  switch (S_) {                                  \
+    case 1: { constexpr int S = 1; CALL; } break; \
+    case 2: { constexpr int S = 2; CALL; } break; \
+    case 3: { constexpr int S = 3; CALL; } break; \
+    case 4: { constexpr int S = 4; CALL; } break; \
+    case 5: { constexpr int S = 5; CALL; } break; \
+    case 6: { constexpr int S = 6; CALL; } break; \
+    case 7: { constexpr int S = 7; CALL; } break; \
+    case 8: { constexpr int S = 8; CALL; } break; \
+    default: return HSP_EINVAL;                  \
+  }
+
+static bool bad_dims(int B, int N, int k, int S, int C) {
+  return B < 0 || N <= 0 || k <= 0 || k > GC_MAXK || S < 1 || S > 8 || C <= 0 || B > 65535;
+}
+
+}  // namespace hsp
+
+extern "C" int hsp_surface_conv_fwd(const float* xyz, const int32_t* idx, const float* dirn,
+                                    int B, int N, int k, int S, int C, float* out,
+                                    void* stream) {
+  using namespace hsp;
+  if (!xyz || !idx || !dirn || !out || bad_dims(B, N, k, S, C)) return HSP_EINVAL;
+  if (B == 0) return HSP_OK;
+  dim3 grid((N + GC_PT - 1) / GC_PT, B, (C + GC_THREADS - 1) / GC_THREADS);
+  cudaStream_t st = (cudaStream_t)stream;
+  HSP_DISPATCH_S(S, (surface_conv_fwd_kernel<S><<<grid, GC_THREADS, 0, st>>>(xyz, idx, dirn, N, k, C, out)));
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}
+
+extern "C" int hsp_graph_conv_fwd(const float* xyz, const int32_t* idx, const float* dirn,
+                                  const float* P, int B, int N, int k, int S, int C,
+                                  float* out, uint8_t* argmax, void* stream) {
+  using namespace hsp;
+  if (!xyz || !idx || !dirn || !P || !out || bad_dims(B, N, k, S, C)) return HSP_EINVAL;
+  if (argmax && k > 255) return HSP_EINVAL;
+  if (B == 0) return HSP_OK;
+  dim3 grid((N + GC_PT - 1) / GC_PT, B, (C + GC_THREADS - 1) / GC_THREADS);
+  cudaStream_t st = (cudaStream_t)stream;
+  HSP_DISPATCH_S(S, (graph_conv_fwd_kernel<S><<<grid, GC_THREADS, 0, st>>>(xyz, idx, dirn, P, N, k, C, out, argmax)));
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}
+
+extern "C" size_t hsp_surface_conv_bwd_workspace_bytes(int B, int N, int k, int S, int C) {
+  using namespace hsp;
+  if (bad_dims(B, N, k, S, C) || B == 0) return 0;
+  return (size_t)bwd_ctas(B, N) * 3 * S * C * sizeof(float);
+}
+extern "C" size_t hsp_graph_conv_bwd_workspace_bytes(int B, int N, int k, int S, int C) {
+  return hsp_surface_conv_bwd_workspace_bytes(B, N, k, S, C);
+}
+
+extern "C" int hsp_surface_conv_bwd(const float* xyz, const int32_t* idx, const float* dirn,
+                                    const float* gout, int B, int N, int k, int S, int C,
+                                    float* gdirn, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  using namespace hsp;
+  if (!xyz || !idx || !dirn || !gout || !gdirn || bad_dims(B, N, k, S, C)) return HSP_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) {
+    return cudaMemsetAsync(gdirn, 0, sizeof(float) * 3 * S * C, st) == cudaSuccess ? HSP_OK
+                                                                                   : HSP_ELAUNCH;
+  }
+  if (!workspace || workspace_bytes < hsp_surface_conv_bwd_workspace_bytes(B, N, k, S, C))
+    return HSP_EWORKSPACE;
+  const int ctas = bwd_ctas(B, N);
+  dim3 grid(ctas, 1, (C + GC_THREADS - 1) / GC_THREADS);
+  HSP_DISPATCH_S(S, (surface_conv_bwd_kernel<S><<<grid, GC_THREADS, 0, st>>>(
+                        xyz, idx, dirn, gout, B, N, k, C, (float*)workspace)));
+  HSP_LAUNCH_CHECK();
+  const int cols = 3 * S * C;
+  dir_reduce_kernel<<<(cols + 127) / 128, 128, 0, st>>>((const float*)workspace, ctas, cols, gdirn);
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}
+
+extern "C" int hsp_graph_conv_bwd(const float* xyz, const int32_t* idx, const float* dirn,
+                                  const float* P, const uint8_t* argmax, const float* gout,
+                                  int B, int N, int k, int S, int C, float* gP, float* gdirn,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace hsp;
+  if (!xyz || !idx || !dirn || !P || !argmax || !gout || !gP || !gdirn ||
+      bad_dims(B, N, k, S, C))
+    return HSP_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) {
+    return cudaMemsetAsync(gdirn, 0, sizeof(float) * 3 * S * C, st) == cudaSuccess ? HSP_OK
+                                                                                   : HSP_ELAUNCH;
+  }
+  if (!workspace || workspace_bytes < hsp_graph_conv_bwd_workspace_bytes(B, N, k, S, C))
+    return HSP_EWORKSPACE;
+  if (cudaMemsetAsync(gP, 0, sizeof(float) * (size_t)B * N * (S + 1) * C, st) != cudaSuccess)
+    return HSP_ELAUNCH;
+  const int ctas = bwd_ctas(B, N);
+  dim3 grid(ctas, 1, (C + GC_THREADS - 1) / GC_THREADS);
+  HSP_DISPATCH_S(S, (graph_conv_bwd_kernel<S><<<grid, GC_THREADS, 0, st>>>(
+                        xyz, idx, dirn, P, argmax, gout, B, N, k, C, gP, (float*)workspace)));
+  HSP_LAUNCH_CHECK();
+  const int cols = 3 * S * C;
+  dir_reduce_kernel<<<(cols + 127) / 128, 128, 0, st>>>((const float*)workspace, ctas, cols, gdirn);
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}
+
+extern "C" int hsp_neighbor_direction_norm(const float* xyz, const int32_t* idx, int B, int N,
+                                           int k, float* out_norm, float* out_raw,
+                                           void* stream) {
+  using namespace hsp;
+  if (!xyz || !idx || !out_norm || B < 0 || N <= 0 || k <= 0) return HSP_EINVAL;
+  if ((long)B * N * k > 0x7fffffffL) return HSP_EINVAL;
+  const int total = B * N * k;
+  if (total == 0) return HSP_OK;
+  direction_norm_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      xyz, idx, N, k, total, out_norm, out_raw);
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}

@@ -1,0 +1,327 @@
+"""Torch-facing wrappers over the C ABI (include/hspose_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; every op below
+is one or two launches of a hand-written sm_100a kernel in libhspose_b200.so.
+No op has a PyTorch/CPU fallback — a missing library or a CPU tensor raises.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+DIST_NEIGHBOR = 0
+DIST_NEAREST = 1
+
+_launches = 0  # number of C-ABI kernel-launching calls issued (bench.py reads this)
+
+
+def launch_count():
+    return _launches
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need(t, dtype, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.HSPoseLibraryError(
+            f"{name}: expected a CUDA tensor (hs-pose_b200 has no CPU path), got "
+            f"{type(t).__name__} on {getattr(t, 'device', '?')}")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _call(name, *args):
+    global _launches
+    lib = _lib.load()
+    _launches += 1
+    _lib.check(getattr(lib, name)(*args), name)
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------- KNN
+def knn3(query, cand, k, drop_first=1, formula=DIST_NEIGHBOR, want64=False, want32=True):
+    """Fused 3-D distance + top-k (K1).  Returns (idx64 | None, idx32 | None)."""
+    query = _need(query, torch.float32, "query")
+    cand = _need(cand, torch.float32, "cand")
+    B, M, D = query.shape
+    if D != 3 or cand.shape[0] != B or cand.shape[2] != 3:
+        raise ValueError("knn3 expects (B,M,3) and (B,N,3)")
+    N = cand.shape[1]
+    with torch.cuda.device(query.device):
+        i64 = torch.empty(B, M, k, dtype=torch.int64, device=query.device) if want64 else None
+        i32 = torch.empty(B, M, k, dtype=torch.int32, device=query.device) if want32 else None
+        _call("hsp_knn3", _p(query), _p(cand), B, M, N, k, drop_first, formula, _p(i64), _p(i32),
+              _stream())
+    return i64, i32
+
+
+def knn_feat(feat, k, drop_first=1, want64=False, want32=True):
+    """Fused D-dim (feature-space) distance + top-k (K2)."""
+    feat = _need(feat, torch.float32, "feat")
+    B, N, D = feat.shape
+    with torch.cuda.device(feat.device):
+        lib = _lib.load()
+        ws = _workspace(lib.hsp_knn_feat_workspace_bytes(B, N), feat.device)
+        i64 = torch.empty(B, N, k, dtype=torch.int64, device=feat.device) if want64 else None
+        i32 = torch.empty(B, N, k, dtype=torch.int32, device=feat.device) if want32 else None
+        _call("hsp_knn_feat", _p(feat), B, N, D, k, drop_first, _p(i64), _p(i32), _p(ws),
+              ws.numel(), _stream())
+    return i64, i32
+
+
+def direction_norm(xyz, idx32, return_unnormed=False):
+    xyz = _need(xyz, torch.float32, "xyz")
+    idx32 = _need(idx32, torch.int32, "idx")
+    B, N, k = idx32.shape
+    with torch.cuda.device(xyz.device):
+        out = torch.empty(B, N, k, 3, dtype=torch.float32, device=xyz.device)
+        raw = torch.empty_like(out) if return_unnormed else None
+        _call("hsp_neighbor_direction_norm", _p(xyz), _p(idx32), B, N, k, _p(out), _p(raw),
+              _stream())
+    return (out, raw) if return_unnormed else out
+
+
+# ------------------------------------------------------------ graph convs
+class _SurfaceConv(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, xyz, idx32, dirn, S, C):
+        xyz = _need(xyz, torch.float32, "xyz")
+        idx32 = _need(idx32, torch.int32, "idx")
+        dirn = _need(dirn, torch.float32, "dirn")
+        B, N, k = idx32.shape
+        with torch.cuda.device(xyz.device):
+            out = torch.empty(B, N, C, dtype=torch.float32, device=xyz.device)
+            _call("hsp_surface_conv_fwd", _p(xyz), _p(idx32), _p(dirn), B, N, k, S, C, _p(out),
+                  _stream())
+        ctx.save_for_backward(xyz, idx32, dirn)
+        ctx.dims = (B, N, k, S, C)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        xyz, idx32, dirn = ctx.saved_tensors
+        B, N, k, S, C = ctx.dims
+        gout = _need(gout.float(), torch.float32, "gout")
+        with torch.cuda.device(xyz.device):
+            lib = _lib.load()
+            ws = _workspace(lib.hsp_surface_conv_bwd_workspace_bytes(B, N, k, S, C), xyz.device)
+            gdirn = torch.empty_like(dirn)
+            _call("hsp_surface_conv_bwd", _p(xyz), _p(idx32), _p(dirn), _p(gout), B, N, k, S, C,
+                  _p(gdirn), _p(ws), ws.numel(), _stream())
+        return None, None, gdirn, None, None
+
+
+def surface_conv(xyz, idx32, dirn, S, C):
+    """K3: out (B,N,C) = mean_s max_n relu(rhat . dirn)."""
+    return _SurfaceConv.apply(xyz, idx32, dirn, S, C)
+
+
+class _GraphConv(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, xyz, idx32, dirn, P, S, C):
+        xyz = _need(xyz, torch.float32, "xyz")
+        idx32 = _need(idx32, torch.int32, "idx")
+        dirn = _need(dirn, torch.float32, "dirn")
+        P = _need(P, torch.float32, "P")
+        B, N, k = idx32.shape
+        if P.shape != (B, N, (S + 1) * C):
+            raise ValueError(f"P must be (B,N,(S+1)*C), got {tuple(P.shape)}")
+        need_grad = any(ctx.needs_input_grad)
+        with torch.cuda.device(xyz.device):
+            out = torch.empty(B, N, C, dtype=torch.float32, device=xyz.device)
+            am = torch.empty(B, N, S * C, dtype=torch.uint8, device=xyz.device) if need_grad else None
+            _call("hsp_graph_conv_fwd", _p(xyz), _p(idx32), _p(dirn), _p(P), B, N, k, S, C,
+                  _p(out), _p(am), _stream())
+        if need_grad:
+            ctx.save_for_backward(xyz, idx32, dirn, P, am)
+        ctx.dims = (B, N, k, S, C)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        xyz, idx32, dirn, P, am = ctx.saved_tensors
+        B, N, k, S, C = ctx.dims
+        gout = _need(gout.float(), torch.float32, "gout")
+        with torch.cuda.device(xyz.device):
+            lib = _lib.load()
+            ws = _workspace(lib.hsp_graph_conv_bwd_workspace_bytes(B, N, k, S, C), xyz.device)
+            gP = torch.empty_like(P)
+            gdirn = torch.empty_like(dirn)
+            _call("hsp_graph_conv_bwd", _p(xyz), _p(idx32), _p(dirn), _p(P), _p(am), _p(gout),
+                  B, N, k, S, C, _p(gP), _p(gdirn), _p(ws), ws.numel(), _stream())
+        return None, None, gdirn, gP, None, None
+
+
+def graph_conv(xyz, idx32, dirn, P, S, C):
+    """K4: out = P[..., :C] + mean_s max_n(relu(rhat . dirn) * P[idx, C + s*C + c])."""
+    return _GraphConv.apply(xyz, idx32, dirn, P, S, C)
+
+
+# ---------------------------------------------------------------- gathers
+class _GatherMax(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, feat, idx32, rows32, kuse):
+        feat = _need(feat, torch.float32, "feat")
+        idx32 = _need(idx32, torch.int32, "idx")
+        B, N, C = feat.shape
+        kstride = idx32.shape[2]
+        R = N if rows32 is None else rows32.numel()
+        if rows32 is not None:
+            rows32 = _need(rows32, torch.int32, "rows")
+        need_grad = ctx.needs_input_grad[0]
+        with torch.cuda.device(feat.device):
+            out = torch.empty(B, R, C, dtype=torch.float32, device=feat.device)
+            am = torch.empty(B, R, C, dtype=torch.uint8, device=feat.device) if need_grad else None
+            _call("hsp_gather_max_fwd", _p(feat), _p(idx32), _p(rows32), B, N, C, R, kuse,
+                  kstride, _p(out), _p(am), _stream())
+        if need_grad:
+            ctx.save_for_backward(idx32, rows32, am)
+        ctx.dims = (B, N, C, R, kuse, kstride)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        idx32, rows32, am = ctx.saved_tensors
+        B, N, C, R, kuse, kstride = ctx.dims
+        gout = _need(gout.float(), torch.float32, "gout")
+        with torch.cuda.device(gout.device):
+            gfeat = torch.zeros(B, N, C, dtype=torch.float32, device=gout.device)
+            _call("hsp_gather_max_bwd", _p(gout), _p(idx32), _p(rows32), _p(am), B, N, C, R,
+                  kuse, kstride, _p(gfeat), _stream())
+        return gfeat, None, None, None
+
+
+def gather_max(feat, idx32, rows32=None, kuse=None):
+    """K5b: out[b,r,c] = max_{n<kuse} feat[b, idx[b, rows[r], n], c]."""
+    return _GatherMax.apply(feat, idx32, rows32, idx32.shape[2] if kuse is None else kuse)
+
+
+class _OrlGlobal(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, feat, idx32):
+        feat = _need(feat, torch.float32, "feat")
+        idx32 = _need(idx32, torch.int32, "idx")
+        B, N, C = feat.shape
+        k = idx32.shape[2]
+        need_grad = ctx.needs_input_grad[0]
+        with torch.cuda.device(feat.device):
+            lib = _lib.load()
+            ws = _workspace(lib.hsp_orl_global_workspace_bytes(B, N, C), feat.device)
+            G = torch.empty(B, C, dtype=torch.float32, device=feat.device)
+            am = torch.empty(B, N, C, dtype=torch.uint8, device=feat.device) if need_grad else None
+            _call("hsp_orl_global_fwd", _p(feat), _p(idx32), B, N, C, k, _p(G), _p(am), _p(ws),
+                  ws.numel(), _stream())
+        if need_grad:
+            ctx.save_for_backward(idx32, am)
+        ctx.dims = (B, N, C, k)
+        return G
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gG):
+        idx32, am = ctx.saved_tensors
+        B, N, C, k = ctx.dims
+        gG = _need(gG.float(), torch.float32, "gG")
+        with torch.cuda.device(gG.device):
+            gfeat = torch.zeros(B, N, C, dtype=torch.float32, device=gG.device)
+            _call("hsp_orl_global_bwd", _p(gG), _p(idx32), _p(am), B, N, C, k, _p(gfeat),
+                  _stream())
+        return gfeat, None
+
+
+def orl_global(feat, idx32):
+    """K5a: G (B,C) = mean_i max_n feat[b, idx[b,i,n], c]."""
+    return _OrlGlobal.apply(feat, idx32)
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, feat, nn32):
+        feat = _need(feat, torch.float32, "feat")
+        nn32 = _need(nn32, torch.int32, "nn")
+        B, Nsrc, C = feat.shape
+        M = nn32.shape[1]
+        with torch.cuda.device(feat.device):
+            out = torch.empty(B, M, C, dtype=torch.float32, device=feat.device)
+            _call("hsp_upsample_rows_fwd", _p(feat), _p(nn32), B, Nsrc, M, C, _p(out), C, 0,
+                  _stream())
+        ctx.save_for_backward(nn32)
+        ctx.dims = (B, Nsrc, M, C)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        (nn32,) = ctx.saved_tensors
+        B, Nsrc, M, C = ctx.dims
+        gout = _need(gout.float(), torch.float32, "gout")
+        with torch.cuda.device(gout.device):
+            gfeat = torch.zeros(B, Nsrc, C, dtype=torch.float32, device=gout.device)
+            _call("hsp_upsample_rows_bwd", _p(gout), _p(nn32), B, Nsrc, M, C, C, 0, _p(gfeat),
+                  _stream())
+        return gfeat, None
+
+
+def gather_rows(feat, nn32):
+    """K5c: out[b,i,:] = feat[b, nn[b,i], :]   (nn (B,M) int32)."""
+    return _GatherRows.apply(feat, nn32)
+
+
+# ---------------------------------------------------------------- chamfer
+class _Chamfer(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, a, b):
+        a = _need(a, torch.float32, "a")
+        b = _need(b, torch.float32, "b")
+        B, N, _ = a.shape
+        M = b.shape[1]
+        with torch.cuda.device(a.device):
+            da = torch.empty(B, N, dtype=torch.float32, device=a.device)
+            db = torch.empty(B, M, dtype=torch.float32, device=a.device)
+            ia = torch.empty(B, N, dtype=torch.int32, device=a.device)
+            ib = torch.empty(B, M, dtype=torch.int32, device=a.device)
+            _call("hsp_chamfer_fwd", _p(a), _p(b), B, N, M, _p(da), _p(ia), _p(db), _p(ib),
+                  _stream())
+        ctx.save_for_backward(a, b, ia, ib)
+        ctx.mark_non_differentiable(ia, ib)
+        return da, db, ia, ib
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gda, gdb, _gia, _gib):
+        a, b, ia, ib = ctx.saved_tensors
+        B, N, _ = a.shape
+        M = b.shape[1]
+        gda = _need(gda.float(), torch.float32, "gda")
+        gdb = _need(gdb.float(), torch.float32, "gdb")
+        with torch.cuda.device(a.device):
+            ga = torch.empty_like(a)
+            gb = torch.empty_like(b)
+            _call("hsp_chamfer_bwd", _p(a), _p(b), _p(ia), _p(ib), _p(gda), _p(gdb), B, N, M,
+                  _p(ga), _p(gb), _stream())
+        return ga, gb
+
+
+def chamfer(a, b):
+    """K7: (dist_a (B,N), dist_b (B,M), idx_a, idx_b) squared NN distances both ways."""
+    return _Chamfer.apply(a, b)

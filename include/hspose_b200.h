@@ -1,0 +1,167 @@
+/*
+ * hspose_b200.h — C ABI of libhspose_b200.so (sm_100a only).
+ *
+ * Drop-in boundary for the HS-Pose hybrid-scope feature extractor.  The
+ * reference (Lynne-Zheng-Linfang/HS-Pose) has no FFI of its own: the hot path
+ * is the Python module network/fs_net_repo/gcn3d.py.  Every entry point below
+ * therefore cites the gcn3d.py function (file:line) whose arithmetic it
+ * replaces; INTEGRATION.md shows the ctypes stub a maintainer adds to gcn3d.py.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers, contiguous row-major, borrowed;
+ *     outputs are caller-allocated; the library never allocates user-visible
+ *     memory.  Scratch comes from a caller-provided workspace whose size is
+ *     returned by the matching *_workspace_bytes() query.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     re-entrant, and never synchronises the device.
+ *   - return value: 0 (HSP_OK) or a negative HSP_E* code; hsp_strerror()
+ *     gives the text.  No exceptions, no printf.
+ *   - float = IEEE fp32.  Neighbour indices are int32 inside the library;
+ *     int64 copies (the dtype torch.topk returns) are optional outputs.
+ */
+#ifndef HSPOSE_B200_H_
+#define HSPOSE_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSP_OK          0
+#define HSP_EINVAL     -1   /* bad argument (null pointer, k > n, unsupported size) */
+#define HSP_ELAUNCH    -2   /* kernel launch failed (cudaGetLastError != success)  */
+#define HSP_EDEVICE    -3   /* device is not sm_100 (Blackwell B200)               */
+#define HSP_EWORKSPACE -4   /* workspace too small / missing                       */
+
+/* Distance formulas (evaluation order matters: KNN indices are bit-exact). */
+#define HSP_DIST_NEIGHBOR 0 /* ((-2*inner) + q[j]) + q[i]     gcn3d.py:19-21 */
+#define HSP_DIST_NEAREST  1 /* (s[j] + t[i]) - (2*inner)      gcn3d.py:31-34 */
+
+int         hsp_version(void);
+const char* hsp_strerror(int code);
+/* 0 if the current device is compute capability 10.x, else HSP_EDEVICE. */
+int         hsp_device_check(void);
+
+/* ------------------------------------------------------------------ K1 ---
+ * Fused 3-D pairwise distance + top-k.  Replaces
+ *   get_neighbor_index(vertices, k)   gcn3d.py:15-24  (formula NEIGHBOR, drop_first=1)
+ *   get_nearest_index(target, source) gcn3d.py:27-36  (formula NEAREST, k=1, drop_first=0)
+ * query (B,M,3), cand (B,N,3) (may alias).  For every query the k+drop_first
+ * smallest distances are selected (ascending; ties broken by lower index) and
+ * the first `drop_first` are discarded, exactly as `topk(k+1)[..., 1:]`.
+ * idx64 (B,M,k) and/or idx32 (B,M,k) receive the indices (either may be NULL).
+ * Never materialises the MxN matrix.  Requires k+drop_first <= min(N,64),
+ * N <= 8192.                                                              */
+int hsp_knn3(const float* query, const float* cand, int B, int M, int N, int k,
+             int drop_first, int formula, int64_t* idx64, int32_t* idx32,
+             void* stream);
+
+/* ------------------------------------------------------------------ K2 ---
+ * Fused D-dimensional (feature-space, "RF-F") distance + top-k. Replaces
+ *   get_neighbor_index(feature_map, k) gcn3d.py:15-24 with D in {128,256,...}
+ * feat (B,N,D), D % 32 == 0.  inner[i,j] is accumulated as ONE sequential FP32
+ * FMA chain over d = 0..D-1; |f|^2 as rounded squares added left to right;
+ * formula NEIGHBOR.  workspace: B*N floats (row norms).                      */
+size_t hsp_knn_feat_workspace_bytes(int B, int N);
+int hsp_knn_feat(const float* feat, int B, int N, int D, int k, int drop_first,
+                 int64_t* idx64, int32_t* idx32, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* get_neighbor_direction_norm (gcn3d.py:49-59) materialised (API parity only;
+ * K3/K4 compute it in-kernel): out_norm (B,N,k,3) = F.normalize(nbr - centre),
+ * out_raw (B,N,k,3) optional un-normalised differences.                     */
+int hsp_neighbor_direction_norm(const float* xyz, const int32_t* idx, int B, int N,
+                                int k, float* out_norm, float* out_raw, void* stream);
+
+/* ------------------------------------------------------------------ K3 ---
+ * Surface graph-convolution (HSlayer_surface.graph_conv, gcn3d.py:92-107):
+ *   out[b,i,c] = 1/S * sum_s max_n relu( rhat[b,i,n] . dirn[:, s*C+c] )
+ * rhat = normalize(xyz[idx[b,i,n]] - xyz[b,i])  (gcn3d.py:49-59), computed
+ * in-kernel.  xyz (B,N,3); idx (B,N,k) int32; dirn (3,S*C) already
+ * column-normalised (F.normalize(directions, dim=0)); out (B,N,C).         */
+int hsp_surface_conv_fwd(const float* xyz, const int32_t* idx, const float* dirn,
+                         int B, int N, int k, int S, int C, float* out, void* stream);
+/* grad wrt dirn: gdirn (3,S*C) (overwritten).  Deterministic two-stage
+ * reduction through `workspace`.                                           */
+size_t hsp_surface_conv_bwd_workspace_bytes(int B, int N, int k, int S, int C);
+int hsp_surface_conv_bwd(const float* xyz, const int32_t* idx, const float* dirn,
+                         const float* gout, int B, int N, int k, int S, int C,
+                         float* gdirn, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ------------------------------------------------------------------ K4 ---
+ * HS graph-convolution (HS_layer.graph_conv, gcn3d.py:158-181):
+ *   out[b,i,c] = P[b,i,c] + 1/S * sum_s max_n( relu(rhat[b,i,n].dirn[:,s*C+c])
+ *                                              * P[b, idx[b,i,n], C + s*C + c] )
+ * P (B,N,(S+1)*C) = feature_map @ weights + bias (dense GEMM done by the
+ * caller); idx = feature-space neighbours; rhat from xyz of those neighbours.
+ * argmax (B,N,S*C) uint8 (optional, may be NULL) receives the winning n for
+ * the backward pass.                                                        */
+int hsp_graph_conv_fwd(const float* xyz, const int32_t* idx, const float* dirn,
+                       const float* P, int B, int N, int k, int S, int C,
+                       float* out, uint8_t* argmax, void* stream);
+/* Backward: gP (B,N,(S+1)*C) (overwritten: centre part = gout, support part
+ * = scatter of gout/S*theta to the winning neighbour rows), gdirn (3,S*C).  */
+size_t hsp_graph_conv_bwd_workspace_bytes(int B, int N, int k, int S, int C);
+int hsp_graph_conv_bwd(const float* xyz, const int32_t* idx, const float* dirn,
+                       const float* P, const uint8_t* argmax, const float* gout,
+                       int B, int N, int k, int S, int C, float* gP, float* gdirn,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ K5 ---
+ * Row gather + max over neighbours, evaluated at selected rows only:
+ *   out[b,r,c] = max_{n<kuse} feat[b, idx[b, rows[r], n], c]
+ * rows == NULL means rows[r] = r (R must equal N).  idx has row stride
+ * kstride >= kuse (a k=20 neighbour table serves the k=4 pooling).  Replaces
+ *   Pool_layer.forward       gcn3d.py:234-246  (rows = randperm sample)
+ *   get_ORL_global max part  gcn3d.py:213-216
+ * argmax (B,R,C) uint8 optional.                                            */
+int hsp_gather_max_fwd(const float* feat, const int32_t* idx, const int32_t* rows,
+                       int B, int N, int C, int R, int kuse, int kstride,
+                       float* out, uint8_t* argmax, void* stream);
+/* gfeat (B,N,C) += scatter(gout) ; gfeat must be zero-initialised by caller
+ * (or hold a gradient to accumulate into).                                  */
+int hsp_gather_max_bwd(const float* gout, const int32_t* idx, const int32_t* rows,
+                       const uint8_t* argmax, int B, int N, int C, int R, int kuse,
+                       int kstride, float* gfeat, void* stream);
+
+/* ORL global descriptor (get_ORL_global, gcn3d.py:211-218):
+ *   G[b,c] = 1/N * sum_i max_n feat[b, idx[b,i,n], c]          G (B,C)
+ * Deterministic: per-CTA partial sums go through `workspace`.               */
+size_t hsp_orl_global_workspace_bytes(int B, int N, int C);
+int hsp_orl_global_fwd(const float* feat, const int32_t* idx, int B, int N, int C,
+                       int k, float* G, uint8_t* argmax, void* workspace,
+                       size_t workspace_bytes, void* stream);
+/* gfeat (B,N,C) += scatter(gG[b,c]/N) to the winning rows.                  */
+int hsp_orl_global_bwd(const float* gG, const int32_t* idx, const uint8_t* argmax,
+                       int B, int N, int C, int k, float* gfeat, void* stream);
+
+/* Nearest-neighbour up-sampling (FaceRecon.py:100-104):
+ *   out[b,i, col0:col0+C] = feat[b, nn[b,i], :]     out row stride = ldo
+ * writes straight into the (B,M,ldo) concat buffer.                         */
+int hsp_upsample_rows_fwd(const float* feat, const int32_t* nn, int B, int Nsrc,
+                          int M, int C, float* out, int ldo, int col0, void* stream);
+/* gfeat (B,Nsrc,C) += sum over i with nn[b,i]==r of gout[b,i,col0:col0+C].   */
+int hsp_upsample_rows_bwd(const float* gout, const int32_t* nn, int B, int Nsrc,
+                          int M, int C, int ldo, int col0, float* gfeat, void* stream);
+
+/* ------------------------------------------------------------------ K7 ---
+ * Chamfer distance (tools/pyTorchChamferDistance/chamfer_distance.cu:6-187):
+ * for each point of a (B,N,3) the squared distance to / index of the nearest
+ * point of b (B,M,3) and vice versa.  Direct (x-y)^2 sums as in the reference
+ * kernel.                                                                   */
+int hsp_chamfer_fwd(const float* a, const float* b, int B, int N, int M,
+                    float* dist_a, int32_t* idx_a, float* dist_b, int32_t* idx_b,
+                    void* stream);
+/* ga (B,N,3), gb (B,M,3) overwritten.  The scatter to the matched point uses
+ * float atomics, like the reference's ChamferDistanceGradKernel (:158-187).  */
+int hsp_chamfer_bwd(const float* a, const float* b, const int32_t* idx_a,
+                    const int32_t* idx_b, const float* gdist_a, const float* gdist_b,
+                    int B, int N, int M, float* ga, float* gb, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSPOSE_B200_H_ */

@@ -1,0 +1,270 @@
+"""GPU parity (T1, kernel level): every C-ABI kernel against the oracle and the
+reference-generated golden vectors, on identical inputs.
+
+Bars: KNN indices bit-exact (under exact distance ties: identical distance
+lists); float outputs within 1e-5 absolute (north_star tolerance)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle as co
+from oracle import torch_oracle as to
+
+pytestmark = pytest.mark.gpu
+
+ATOL = 1e-5
+
+
+def _ops():
+    import hspose_b200.ops as ops
+    return ops
+
+
+def _t(a, dev, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    return t.to(dtype) if dtype is not None else t
+
+
+def test_library_loads_and_is_sm100(cuda):
+    from hspose_b200 import _lib
+    lib = _lib.load()
+    assert lib.hsp_version() >= 100
+    assert lib.hsp_device_check() == 0
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+def test_cpu_tensor_is_rejected(cuda):
+    from hspose_b200 import _lib
+    with pytest.raises(_lib.HSPoseLibraryError):
+        _ops().knn3(torch.zeros(1, 8, 3), torch.zeros(1, 8, 3), 2)
+
+
+# ----------------------------------------------------------------- K1
+def test_knn3_golden_bit_exact(cuda, golden):
+    ops, g = _ops(), golden("knn")
+    v = _t(g["c_xyz"], cuda)
+    for k in (4, 8, 20, 32):
+        i64, i32 = ops.knn3(v, v, k, want64=True)
+        assert np.array_equal(i64.cpu().numpy(), g[f"c_idx_k{k}"])
+        assert np.array_equal(i32.cpu().numpy(), g[f"c_idx_k{k}"])
+    p = _t(g["p_xyz"], cuda)
+    assert np.array_equal(ops.knn3(p, p, 8)[1].cpu().numpy(), g["p_idx_k8"])
+    for m in (75, 18):
+        s = _t(g[f"n_src{m}"], cuda)
+        nn = ops.knn3(v, s, 1, drop_first=0, formula=ops.DIST_NEAREST)[1]
+        assert np.array_equal(nn.cpu().numpy(), g[f"n_idx{m}"])
+
+
+def test_knn3_ties_distance_lists(cuda, golden):
+    ops, g = _ops(), golden("knn")
+    for key, gk in (("u_xyz", "u_idx_k20"), ("t_xyz", "t_idx_k20")):
+        mine = ops.knn3(_t(g[key], cuda), _t(g[key], cuda), 20)[1].cpu().numpy()
+        dist = to.pairwise_neighbor_dist(torch.from_numpy(g[key])).numpy()
+        a = np.take_along_axis(dist, mine.astype(np.int64), 2)
+        b = np.take_along_axis(dist, g[gk].astype(np.int64), 2)
+        assert np.array_equal(a, b)
+        # and bit-exact against the C oracle, which shares the (distance, index) tie rule
+        assert np.array_equal(mine, co.neighbor_index(g[key], 20))
+
+
+@pytest.mark.parametrize("B,N,k", [(4, 1028, 20), (3, 257, 20), (5, 64, 8), (2, 1028, 16),
+                                   (1, 4096, 32), (2, 2048, 8), (2, 33, 32), (1, 5, 4)])
+def test_knn3_vs_oracle(cuda, B, N, k):
+    ops = _ops()
+    g = torch.Generator().manual_seed(N * 131 + k)
+    v = torch.randn(B, N, 3, generator=g) * 0.05
+    got = ops.knn3(v.to(cuda), v.to(cuda), k, want64=True)[0].cpu().numpy()
+    assert np.array_equal(got, co.neighbor_index(v.numpy(), k))
+
+
+def test_knn3_nearest_vs_oracle(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    t = torch.randn(3, 1028, 3, generator=g) * 0.05
+    for m in (257, 64):
+        s = t[:, torch.randperm(1028, generator=g)[:m]].contiguous()
+        got = ops.knn3(t.to(cuda), s.to(cuda), 1, drop_first=0, formula=ops.DIST_NEAREST,
+                       want64=True)[0].cpu().numpy()
+        assert np.array_equal(got, co.nearest_index(t.numpy(), s.numpy()))
+
+
+def test_knn3_bad_args(cuda):
+    from hspose_b200 import _lib
+    ops = _ops()
+    v = torch.zeros(1, 8, 3, device=cuda)
+    with pytest.raises(_lib.HSPoseLibraryError):
+        ops.knn3(v, v, 8)  # k + 1 > N
+    with pytest.raises(_lib.HSPoseLibraryError):
+        ops.knn3(v, v, 2, formula=7)
+
+
+# ----------------------------------------------------------------- K2
+def test_knn_feat_golden_and_oracle(cuda, golden):
+    ops, g = _ops(), golden("knn")
+    for key, gk, k in (("f128", "f128_idx_k20", 20), ("f256", "f256_idx_k8", 8)):
+        got = ops.knn_feat(_t(g[key], cuda), k, want64=True)[0].cpu().numpy()
+        assert np.array_equal(got, co.neighbor_index(g[key], k))      # bit-exact vs oracle
+        assert (got == g[gk]).all(axis=2).mean() > 0.97               # reference (MKL order)
+
+
+@pytest.mark.parametrize("B,N,D,k", [(2, 1028, 128, 20), (2, 257, 256, 20), (3, 64, 256, 8),
+                                     (1, 300, 128, 32), (1, 70, 32, 4)])
+def test_knn_feat_vs_oracle(cuda, B, N, D, k):
+    ops = _ops()
+    g = torch.Generator().manual_seed(N + D + k)
+    f = torch.relu(torch.randn(B, N, D, generator=g) + 1.0)
+    got = ops.knn_feat(f.to(cuda), k, want64=True)[0].cpu().numpy()
+    assert np.array_equal(got, co.neighbor_index(f.numpy(), k))
+
+
+# ----------------------------------------------------------------- K3 / K4
+def test_direction_norm(cuda, golden):
+    ops, g = _ops(), golden("ops")
+    out, raw = ops.direction_norm(_t(g["xyz"], cuda), _t(g["idx"], cuda, torch.int32), True)
+    np.testing.assert_allclose(out.cpu().numpy(), g["dir_norm"], atol=1e-6)
+    xyz, idx = g["xyz"], g["idx"].astype(np.int64)
+    nbr = np.stack([xyz[b][idx[b]] for b in range(xyz.shape[0])])
+    assert np.array_equal(raw.cpu().numpy(), nbr - xyz[:, :, None, :])
+
+
+def test_surface_conv_golden(cuda, golden):
+    ops, g = _ops(), golden("ops")
+    d = torch.from_numpy(g["surf_directions"])
+    dirn = torch.nn.functional.normalize(d, dim=0).to(cuda)
+    out = ops.surface_conv(_t(g["xyz"], cuda), _t(g["idx"], cuda, torch.int32), dirn, 7, 16)
+    np.testing.assert_allclose(out.cpu().numpy(), g["surf_out"], atol=ATOL)
+
+
+def test_graph_conv_golden(cuda, golden):
+    ops, g = _ops(), golden("ops")
+    fm, W, bias = (torch.from_numpy(g[n]) for n in ("hs_fm", "hs_weights", "hs_bias"))
+    P = (fm @ W + bias).to(cuda)
+    dirn = torch.nn.functional.normalize(torch.from_numpy(g["hs_directions"]), dim=0).to(cuda)
+    out = ops.graph_conv(_t(g["xyz"], cuda), _t(g["hs_rf_idx"], cuda, torch.int32), dirn, P, 7, 16)
+    np.testing.assert_allclose(out.cpu().numpy(), g["hs_out"], atol=ATOL)
+
+
+@pytest.mark.parametrize("B,N,k,S,C,Cin", [(2, 257, 20, 7, 256, 128), (2, 1028, 20, 7, 128, 128),
+                                           (2, 64, 8, 7, 512, 256), (1, 100, 5, 3, 40, 24)])
+def test_graph_and_surface_conv_fwd_bwd_vs_oracle(cuda, B, N, k, S, C, Cin):
+    """Forward vs the C oracle, backward vs autograd through the materialising
+    torch oracle (CPU, fp32)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(N * 7 + C)
+    xyz = torch.randn(B, N, 3, generator=g) * 0.05
+    fm = torch.relu(torch.randn(B, N, Cin, generator=g))
+    W = ((torch.rand(Cin, (S + 1) * C, generator=g) * 2 - 1) / (C ** 0.5)).requires_grad_()
+    bias = ((torch.rand((S + 1) * C, generator=g) * 2 - 1) * 0.1).requires_grad_()
+    dirs = ((torch.rand(3, S * C, generator=g) * 2 - 1) * 0.3).requires_grad_()
+    idx = torch.from_numpy(co.neighbor_index(fm.numpy(), k))
+    gout = torch.randn(B, N, C, generator=g)
+
+    # --- HS graph conv
+    ref = to.hs_graph_conv(xyz, idx, fm, W, bias, dirs, S, C)
+    ref.backward(gout)
+    dW, db, dd = W.grad.clone(), bias.grad.clone(), dirs.grad.clone()
+    Wc = W.detach().to(cuda).requires_grad_()
+    bc = bias.detach().to(cuda).requires_grad_()
+    dc = dirs.detach().to(cuda).requires_grad_()
+    P = fm.to(cuda) @ Wc + bc
+    out = ops.graph_conv(xyz.to(cuda), idx.to(cuda).int(), torch.nn.functional.normalize(dc, dim=0), P, S, C)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), atol=ATOL)
+    Pn = (fm @ W.detach() + bias.detach()).numpy()
+    dn = torch.nn.functional.normalize(dirs.detach(), dim=0).numpy()
+    np.testing.assert_allclose(out.detach().cpu().numpy(),
+                               co.graph_conv_fwd(xyz.numpy(), idx.numpy(), dn, Pn, S, C), atol=ATOL)
+    out.backward(gout.to(cuda))
+    scale = max(1.0, dW.abs().max().item())
+    np.testing.assert_allclose(Wc.grad.cpu().numpy(), dW.numpy(), atol=2e-5 * scale, rtol=1e-4)
+    np.testing.assert_allclose(bc.grad.cpu().numpy(), db.numpy(), atol=2e-5 * max(1.0, db.abs().max().item()), rtol=1e-4)
+    np.testing.assert_allclose(dc.grad.cpu().numpy(), dd.numpy(), atol=2e-5 * max(1.0, dd.abs().max().item()), rtol=1e-4)
+
+    # --- surface conv (geometric neighbours)
+    dirs.grad = None
+    gi = torch.from_numpy(co.neighbor_index(xyz.numpy(), k))
+    ref = to.surface_graph_conv(xyz, gi, dirs, S, C)
+    ref.backward(gout)
+    dc2 = dirs.detach().to(cuda).requires_grad_()
+    out = ops.surface_conv(xyz.to(cuda), gi.to(cuda).int(), torch.nn.functional.normalize(dc2, dim=0), S, C)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), atol=ATOL)
+    out.backward(gout.to(cuda))
+    np.testing.assert_allclose(dc2.grad.cpu().numpy(), dirs.grad.numpy(),
+                               atol=2e-5 * max(1.0, dirs.grad.abs().max().item()), rtol=1e-4)
+
+
+# ----------------------------------------------------------------- K5
+def test_gather_ops_golden(cuda, golden):
+    ops, g = _ops(), golden("ops")
+    feat = _t(g["orl_feat"], cuda)
+    idx = _t(g["idx"], cuda, torch.int32)
+    np.testing.assert_allclose(ops.orl_global(feat, idx).cpu().numpy(), g["orl_global"], atol=ATOL)
+    rows = _t(g["pool_sample"], cuda, torch.int32)
+    pooled = ops.gather_max(feat, idx, rows, kuse=4)
+    assert np.array_equal(pooled.cpu().numpy(), g["pool_feat"])
+    nn = ops.knn3(_t(g["xyz"], cuda), _t(g["pool_xyz"], cuda), 1, drop_first=0,
+                  formula=ops.DIST_NEAREST)[1]
+    assert np.array_equal(nn.cpu().numpy(), g["up_idx"])
+    up = ops.gather_rows(pooled, nn[..., 0].contiguous())
+    assert np.array_equal(up.cpu().numpy(), g["up_out"])
+
+
+def test_gather_ops_backward_vs_autograd(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    B, N, C, k = 2, 257, 256, 20
+    xyz = torch.randn(B, N, 3, generator=g) * 0.05
+    idx = torch.from_numpy(co.neighbor_index(xyz.numpy(), k))
+    feat = torch.randn(B, N, C, generator=g).requires_grad_()
+    rows = torch.randperm(N, generator=g)[: N // 4]
+    # pool
+    ref = to.take_rows(feat, idx[..., :4]).amax(dim=2)[:, rows]
+    gout = torch.randn(ref.shape, generator=g)
+    ref.backward(gout)
+    fc = feat.detach().to(cuda).requires_grad_()
+    out = ops.gather_max(fc, idx.to(cuda).int(), rows.to(cuda).int(), kuse=4)
+    assert np.array_equal(out.detach().cpu().numpy(), ref.detach().numpy())
+    out.backward(gout.to(cuda))
+    np.testing.assert_allclose(fc.grad.cpu().numpy(), feat.grad.numpy(), atol=1e-5)
+    # ORL
+    feat.grad = None
+    ref = to.take_rows(feat, idx).amax(dim=2).mean(dim=1)
+    gG = torch.randn(B, C, generator=g)
+    ref.backward(gG)
+    fc = feat.detach().to(cuda).requires_grad_()
+    G = ops.orl_global(fc, idx.to(cuda).int())
+    np.testing.assert_allclose(G.detach().cpu().numpy(), ref.detach().numpy(), atol=ATOL)
+    G.backward(gG.to(cuda))
+    np.testing.assert_allclose(fc.grad.cpu().numpy(), feat.grad.numpy(), atol=1e-5)
+    # row gather (nearest up-sampling)
+    feat.grad = None
+    nn = torch.randint(0, N, (B, 1028), generator=g)
+    ref = to.take_rows(feat, nn[..., None]).squeeze(2)
+    go = torch.randn(ref.shape, generator=g)
+    ref.backward(go)
+    fc = feat.detach().to(cuda).requires_grad_()
+    up = ops.gather_rows(fc, nn.to(cuda).int())
+    assert np.array_equal(up.detach().cpu().numpy(), ref.detach().numpy())
+    up.backward(go.to(cuda))
+    np.testing.assert_allclose(fc.grad.cpu().numpy(), feat.grad.numpy(), atol=1e-4)
+
+
+# ----------------------------------------------------------------- K7
+def test_chamfer_vs_oracle(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    a = (torch.randn(3, 1028, 3, generator=g) * 0.05).requires_grad_()
+    b = (torch.randn(3, 700, 3, generator=g) * 0.05).requires_grad_()
+    da, ia = co.chamfer_nn(a.detach().numpy(), b.detach().numpy())
+    db, ib = co.chamfer_nn(b.detach().numpy(), a.detach().numpy())
+    ac, bc = a.detach().to(cuda).requires_grad_(), b.detach().to(cuda).requires_grad_()
+    gda, gdb, gia, gib = ops.chamfer(ac, bc)
+    np.testing.assert_allclose(gda.detach().cpu().numpy(), da, atol=1e-7)
+    np.testing.assert_allclose(gdb.detach().cpu().numpy(), db, atol=1e-7)
+    assert np.array_equal(gia.cpu().numpy(), ia) and np.array_equal(gib.cpu().numpy(), ib)
+    # gradient vs autograd on the materialised formulation
+    d = ((a[:, :, None, :] - b[:, None, :, :]) ** 2).sum(-1)
+    loss = d.min(dim=2)[0].mean() + d.min(dim=1)[0].mean()
+    loss.backward()
+    (gda.mean() + gdb.mean()).backward()
+    np.testing.assert_allclose(ac.grad.cpu().numpy(), a.grad.numpy(), atol=1e-6)
+    np.testing.assert_allclose(bc.grad.cpu().numpy(), b.grad.numpy(), atol=1e-6)
