@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — objects/s (N=1028 points) of the HS-Pose hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+One "step" = one train step over one synthetic batch per GPU: HSPose.forward
+(augmentation, KNN + receptive-field gather + 3D-GCN backbone, dense heads,
+fs_net + Chamfer losses) + backward + gradient all-reduce (N>1) + clip(5) + Adam.
+Workload = BASELINE.json configs[2]: batch 128 per GPU, N=1028, k=20, S=7, bf16
+autocast on the dense GEMMs, fp32 KNN / graph-conv kernels.  Weak scaling: the
+per-GPU batch is fixed, objects are sharded over ranks, no data-path collective.
+
+`value`  : objects/s with the batch already resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same step through the public API with HOST (pinned) inputs — H2D of the
+           12 input tensors and D2H of the loss inside the timed region.
+`roofline`: the dominant hand-written kernel of the step, timed live with CUDA events on its
+           launching stream; achieved = algorithmic bytes / launch time vs MEASURED_PEAKS.json.
+`cpu_baseline`: the oracle port (oracle/train_step.py) of the same step on the host cores,
+           bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "objects/sec (N=1028 pts) fwd+bwd"
+UNIT = "objects/s"
+N_PTS, K_NBR, S_SUP = 1028, 20, 7
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=128, help="objects per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample", type=int, default=4, help="objects per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {"workload": f"train step (fwd+bwd+Adam, fs_net+Chamfer losses) batch={args.batch}/GPU "
+                        f"N={N_PTS} k={K_NBR} S={S_SUP}",
+            "global_batch": args.batch * world, "n_points": N_PTS, "k": K_NBR,
+            "precision": "bf16 autocast dense GEMMs; fp32 KNN/graph-conv kernels"
+            if args.precision == "bf16" else "fp32",
+            "parallelism": f"dp{world} (batch sharded, one NCCL grad all-reduce)",
+            "l2": "per-step working set (>2 GB of activations at batch 128) exceeds the 126 MB L2; "
+                  "no explicit flush"}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock + throttle reasons (NVML) during the timed region."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- roofline
+def _alg_bytes(name, a, train=True):
+    """ALGORITHMIC bytes of one launch (each kernel-boundary input read once, each output
+    written once; fp32, int32 indices) — the per-kernel split of SURVEY.md §8(d)'s formula."""
+    if name == "hsp_graph_conv_fwd":
+        B, N, k, S, C = a[:5]
+        return B * (12 * N + 4 * N * k + 4 * N * (S + 1) * C + 4 * N * C + (N * S * C if train else 0))
+    if name == "hsp_graph_conv_bwd":
+        B, N, k, S, C = a[:5]
+        return B * (12 * N + 4 * N * k + 4 * N * (S + 1) * C + N * S * C + 4 * N * C + 4 * N * (S + 1) * C)
+    if name == "hsp_surface_conv_fwd" or name == "hsp_surface_conv_bwd":
+        B, N, k, S, C = a[:5]
+        return B * (12 * N + 4 * N * k + 4 * N * C)
+    if name == "hsp_knn_feat":
+        B, N, D, k = a[:4]
+        return B * (4 * N * D + 4 * N * k)
+    if name == "hsp_knn3":
+        B, M, N, k = a[:4]
+        return B * (12 * N + 12 * M + 4 * M * k)
+    if name in ("hsp_gather_max_fwd", "hsp_gather_max_bwd"):
+        B, N, C, R, kuse, kstride = a[:6]
+        return B * (4 * N * C + 4 * R * kuse + 5 * R * C)
+    if name in ("hsp_orl_global_fwd", "hsp_orl_global_bwd"):
+        B, N, C, k = a[:4]
+        return B * (4 * N * C + 4 * N * k + N * C + 4 * C)
+    if name in ("hsp_upsample_rows_fwd", "hsp_upsample_rows_bwd"):
+        B, Nsrc, M, C = a[:4]
+        return B * (4 * Nsrc * C + 4 * M * C + 4 * M)
+    if name in ("hsp_chamfer_fwd", "hsp_chamfer_bwd"):
+        B, N, M = a[:3]
+        return B * (12 * (N + M) + 8 * (N + M))
+    return 0
+
+
+def kernel_breakdown(records, steps):
+    agg = {}
+    for name, a, ms in records:
+        key = (name, a[:6])
+        d = agg.setdefault(key, {"ms": 0.0, "n": 0})
+        d["ms"] += ms
+        d["n"] += 1
+    rows = []
+    for (name, a), d in agg.items():
+        rows.append({"kernel": name, "dims": list(a), "launches_per_step": d["n"] / steps,
+                     "ms_per_launch": d["ms"] / d["n"], "ms_per_step": d["ms"] / steps,
+                     "alg_bytes": _alg_bytes(name, a)})
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    return rows
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------- reference / CPU arm
+def cpu_port_throughput(sample_objects, steps, warmup, seed=1):
+    """The oracle port of the SAME train step on the host cores (all threads)."""
+    import torch
+    from oracle.synth import synth_batch
+    from oracle.train_step import OracleTrainer
+    from hspose_b200.HSPose import HSPose
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    tr = OracleTrainer(HSPose("PoseNet_only").state_dict())
+    batch = synth_batch(sample_objects, N_PTS, seed=seed, train=True)
+    torch.manual_seed(1234)
+    for _ in range(warmup):
+        tr.step(batch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step(batch)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return sample_objects / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    val, dt = cpu_port_throughput(args.cpu_sample, steps, warm)
+    sample = (f"{steps} timed + {warm} warm-up train steps of {args.cpu_sample} objects (N={N_PTS}) — "
+              f"bounded sample of the batch-{args.batch} workload; materialising PyTorch port of the "
+              f"reference algorithm (the reference is Python; its tree does not travel)")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, max(world, 1)),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import hspose_b200.ops as ops
+    from hspose_b200 import _lib, parallel
+    from hspose_b200.HSPose import HSPose
+    from oracle.synth import synth_batch  # seeded synthetic inputs only (no oracle compute)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
+    rank, world, local = parallel.init_from_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    _lib.check(_lib.load().hsp_device_check(), "hsp_device_check")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+    torch.manual_seed(0)                       # identical weights on every rank
+    model = HSPose("PoseNet_only", chamfer_w=1.0).to(dev).train()
+    flat = parallel.FlatGradients(model.posenet.parameters())
+    opt = torch.optim.Adam(flat.params, lr=1e-4, fused=True)
+    parallel.seed_all(1234)                    # same Pool_layer permutations on every rank
+
+    B = args.batch
+    host = {k: v.pin_memory() for k, v in synth_batch(B, N_PTS, seed=1 + rank, train=True).items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    amp = args.precision == "bf16"
+
+    def step(batch):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            _, losses = model(**batch, do_loss=True)
+        total = sum(v.reshape(()).float() for grp in losses.values() for v in grp.values())
+        flat.zero()
+        total.backward()
+        flat.all_reduce_mean()
+        flat.clip_(5.0)
+        opt.step()
+        return total
+
+    def step_e2e():
+        batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        return step(batch).item()              # D2H of the loss: 4 bytes, synchronises
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ops.launch_count()
+    ms_step = timed(lambda: step(resident), args.steps)
+    launches = ops.launch_count() - l0
+    clocks = sampler.stop()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # per-kernel CUDA-event timing of the same step (separate instrumented pass)
+    ksteps = min(3, args.steps)
+    ops.enable_timing(True)
+    for _ in range(ksteps):
+        step(resident)
+    torch.cuda.synchronize()
+    rows = kernel_breakdown(ops.timing_records(), ksteps)
+    ops.enable_timing(False)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    top = rows[0]
+    ach = top["alg_bytes"] / (top["ms_per_launch"] * 1e-3) / 1e9
+    own_ms = sum(r["ms_per_step"] for r in rows)
+    roofline = {"bound": "hbm", "kernel": top["kernel"], "dims": top["dims"], "achieved": ach,
+                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "alg_bytes_per_launch": top["alg_bytes"],
+                "ms_per_launch": top["ms_per_launch"], "share_of_step": top["ms_per_step"] / ms_step,
+                "own_kernels_ms_per_step": own_ms,
+                "top_kernels": [{"kernel": r["kernel"], "dims": r["dims"],
+                                 "ms_per_step": round(r["ms_per_step"], 4),
+                                 "GBps": round(r["alg_bytes"] / (r["ms_per_launch"] * 1e-3) / 1e9, 1)}
+                                for r in rows[:8]]}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        val, dt = cpu_port_throughput(args.cpu_sample, 3, 1)
+        cpu = {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"3 timed + 1 warm-up train steps of {args.cpu_sample} objects (N={N_PTS}), "
+                         f"oracle/train_step.py on all host threads"}
+
+    line = {"metric": METRIC, "value": B * world / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if amp else "f32", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks,
+            "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -106,7 +106,8 @@ upsample_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ 
   const int b = blockIdx.y;
   const int i_end = min((int)(blockIdx.x + 1) * GO_PT, M);
   for (int i = blockIdx.x * GO_PT; i < i_end; ++i) {
-    const float* src = feat + ((size_t)b * Nsrc + __ldg(nn + (size_t)b * M + i)) * C;
+    const int r = nn ? __ldg(nn + (size_t)b * M + i) : (Nsrc == 1 ? 0 : i);
+    const float* src = feat + ((size_t)b * Nsrc + r) * C;
     float* dst = out + ((size_t)b * M + i) * ldo + col0;
     for (int c = threadIdx.x; c < C; c += GO_THREADS) dst[c] = __ldg(src + c);
   }
@@ -201,9 +202,10 @@ extern "C" int hsp_upsample_rows_fwd(const float* feat, const int32_t* nn, int B
                                      int M, int C, float* out, int ldo, int col0,
                                      void* stream) {
   using namespace hsp;
-  if (!feat || !nn || !out || B < 0 || Nsrc <= 0 || M < 0 || C <= 0 || col0 < 0 ||
+  if (!feat || !out || B < 0 || Nsrc <= 0 || M < 0 || C <= 0 || col0 < 0 ||
       col0 + C > ldo || B > 65535)
     return HSP_EINVAL;
+  if (!nn && Nsrc != 1 && Nsrc != M) return HSP_EINVAL;  /* identity / broadcast modes */
   if (B == 0 || M == 0) return HSP_OK;
   dim3 grid((M + GO_PT - 1) / GO_PT, B);
   upsample_fwd_kernel<<<grid, GO_THREADS, 0, (cudaStream_t)stream>>>(feat, nn, Nsrc, M, C, out,

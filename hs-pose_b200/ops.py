@@ -13,11 +13,28 @@ from . import _lib
 DIST_NEIGHBOR = 0
 DIST_NEAREST = 1
 
-_launches = 0  # number of C-ABI kernel-launching calls issued (bench.py reads this)
+_launches = 0  # number of CUDA kernels launched through the C ABI (bench.py reads this)
+
+# kernels launched per entry point (memsets not counted)
+_KERNELS_PER_CALL = {"hsp_knn_feat": 2, "hsp_surface_conv_bwd": 2, "hsp_graph_conv_bwd": 2,
+                     "hsp_orl_global_fwd": 2, "hsp_chamfer_fwd": 2, "hsp_chamfer_bwd": 2}
+
+_timing = None  # when a list: (name, int-args, start_event, end_event) per call
 
 
 def launch_count():
     return _launches
+
+
+def enable_timing(on=True):
+    """Record a CUDA-event pair around every C-ABI call on the launching stream."""
+    global _timing
+    _timing = [] if on else None
+
+
+def timing_records():
+    """[(entry point, integer args, milliseconds)] — call after torch.cuda.synchronize()."""
+    return [(n, a, e0.elapsed_time(e1)) for n, a, e0, e1 in (_timing or [])]
 
 
 def _p(t):
@@ -34,14 +51,24 @@ def _need(t, dtype, name):
             f"{name}: expected a CUDA tensor (hs-pose_b200 has no CPU path), got "
             f"{type(t).__name__} on {getattr(t, 'device', '?')}")
     if t.dtype != dtype:
-        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+        if dtype == torch.float32 and t.dtype in (torch.bfloat16, torch.float16):
+            t = t.float()   # autocast hands us half tensors; the kernels compute in fp32
+        else:
+            raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
     return t if t.is_contiguous() else t.contiguous()
 
 
 def _call(name, *args):
     global _launches
     lib = _lib.load()
-    _launches += 1
+    _launches += _KERNELS_PER_CALL.get(name, 1)
+    if _timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(getattr(lib, name)(*args), name)
+        e1.record()
+        _timing.append((name, tuple(a for a in args if isinstance(a, int)), e0, e1))
+        return
     _lib.check(getattr(lib, name)(*args), name)
 
 
@@ -284,6 +311,75 @@ class _GatherRows(torch.autograd.Function):
 def gather_rows(feat, nn32):
     """K5c: out[b,i,:] = feat[b, nn[b,i], :]   (nn (B,M) int32)."""
     return _GatherRows.apply(feat, nn32)
+
+
+class _ConcatUpsample(torch.autograd.Function):
+    """feat (B,M,sum C_i) = cat_i rows(piece_i): piece_i is copied as is (nn None,
+    Nsrc == M), gathered through a nearest-neighbour table nn_i (B,M) int32, or
+    broadcast over points ((B,C) piece).  One launch per piece, straight into
+    the concat buffer (FaceRecon.py:100-107 without the intermediate tensors)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, M, nns, *pieces):
+        pieces = [_need(p, torch.float32, "piece") for p in pieces]
+        B = pieces[0].shape[0]
+        widths = [p.shape[-1] for p in pieces]
+        ldo = sum(widths)
+        dev = pieces[0].device
+        nn32 = []
+        with torch.cuda.device(dev):
+            out = torch.empty(B, M, ldo, dtype=torch.float32, device=dev)
+            col = 0
+            for p, nn, w in zip(pieces, nns, widths):
+                if isinstance(nn, str):  # "bcast": (B,C) -> every point
+                    nsrc, t = 1, None
+                elif nn is None:
+                    nsrc, t = p.shape[1], None
+                    if nsrc != M:
+                        raise ValueError("identity piece must have M rows")
+                else:
+                    nsrc, t = p.shape[1], _need(nn, torch.int32, "nn")
+                nn32.append(t)
+                _call("hsp_upsample_rows_fwd", _p(p), _p(t), B, nsrc, M, w, _p(out), ldo, col,
+                      _stream())
+                col += w
+        ctx.save_for_backward(*[t for t in nn32 if t is not None])
+        ctx.meta = (B, M, ldo, widths, [None if t is None else True for t in nn32],
+                    [isinstance(nn, str) for nn in nns], [p.shape[1] if p.dim() == 3 else 1 for p in pieces])
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        B, M, ldo, widths, has_nn, bcast, nsrcs = ctx.meta
+        saved = list(ctx.saved_tensors)
+        gout = _need(gout.float(), torch.float32, "gout")
+        grads, col = [], 0
+        with torch.cuda.device(gout.device):
+            for i, w in enumerate(widths):
+                if not ctx.needs_input_grad[2 + i]:
+                    grads.append(None)
+                    if has_nn[i]:
+                        saved.pop(0)
+                elif bcast[i]:
+                    grads.append(gout[:, :, col:col + w].sum(dim=1))
+                elif has_nn[i]:
+                    nn = saved.pop(0)
+                    g = torch.zeros(B, nsrcs[i], w, dtype=torch.float32, device=gout.device)
+                    _call("hsp_upsample_rows_bwd", _p(gout), _p(nn), B, nsrcs[i], M, w, ldo, col,
+                          _p(g), _stream())
+                    grads.append(g)
+                else:
+                    grads.append(gout[:, :, col:col + w])
+                col += w
+        return (None, None, *grads)
+
+
+def concat_upsample(pieces, nns, M):
+    """K5c + concat.  pieces[i]: (B,M,C) with nns[i] None, (B,Nsrc,C) with nns[i] a
+    (B,M) int32 nearest table, or (B,C) with nns[i] == "bcast"."""
+    return _ConcatUpsample.apply(M, list(nns), *pieces)
 
 
 # ---------------------------------------------------------------- chamfer

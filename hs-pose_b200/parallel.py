@@ -1,0 +1,90 @@
+"""Data parallelism over the GPUs of one box: one process per GPU, the batch
+axis sharded, ONE all-reduce of the gradients per step.
+
+The reference is single-GPU (engine/train.py:23, script.sh:1) — there is
+nothing to port.  Objects are independent in every hot-path op, so forward and
+backward need no collective; only the 9,709,871 fp32 gradients (38.8 MB) are
+summed over NVLink/NVSwitch with NCCL and divided by the world size, before
+`clip_grad_norm_` (the clip must see the reduced gradient, engine/train.py:107).
+
+`FlatGradients` re-homes every `param.grad` as a view into one contiguous
+buffer, so the collective is a single in-place NCCL call with no pack/unpack
+copies.  BatchNorm statistics stay per replica (the reference has no SyncBN) and
+every rank must draw the same `Pool_layer` permutation: seed the CPU generator
+identically on all ranks (`seed_all`).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's env; returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def seed_all(seed):
+    """Same CPU-generator seed on every rank: Pool_layer's randperm (reference
+    gcn3d.py:243) must select the same rows everywhere to equal one big batch."""
+    torch.manual_seed(seed)
+
+
+def shard_batch(batch, rank, world):
+    """Contiguous split of every (B, ...) tensor along the batch axis."""
+    out = {}
+    for k, v in batch.items():
+        if torch.is_tensor(v) and v.dim() > 0:
+            per = v.shape[0] // world
+            out[k] = v[rank * per:(rank + 1) * per]
+        else:
+            out[k] = v
+    return out
+
+
+class FlatGradients:
+    """All gradients of `params` as views of one flat fp32 buffer + one all-reduce."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+
+    def zero(self):
+        """zero_grad() that keeps the views (never set_to_none)."""
+        self.flat.zero_()
+
+    def all_reduce_mean(self, async_op=False):
+        if self.world == 1:
+            return None
+        if dist.get_backend() == "nccl":
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, async_op=async_op)
+        w = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=False)
+        self.flat.div_(self.world)
+        return w
+
+    def clip_(self, max_norm):
+        """clip_grad_norm_ on the flat buffer (one norm kernel instead of 160)."""
+        total = torch.linalg.vector_norm(self.flat)
+        self.flat.mul_(torch.clamp(max_norm / (total + 1e-6), max=1.0))
+        return total

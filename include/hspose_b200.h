@@ -140,7 +140,9 @@ int hsp_orl_global_bwd(const float* gG, const int32_t* idx, const uint8_t* argma
 
 /* Nearest-neighbour up-sampling (FaceRecon.py:100-104):
  *   out[b,i, col0:col0+C] = feat[b, nn[b,i], :]     out row stride = ldo
- * writes straight into the (B,M,ldo) concat buffer.                         */
+ * writes straight into the (B,M,ldo) concat buffer.  nn == NULL selects the
+ * identity (Nsrc == M: row i) or broadcast (Nsrc == 1: row 0) copy, so the
+ * whole torch.cat of FaceRecon.py:107 is served by this one entry point.    */
 int hsp_upsample_rows_fwd(const float* feat, const int32_t* nn, int B, int Nsrc,
                           int M, int C, float* out, int ldo, int col0, void* stream);
 /* gfeat (B,Nsrc,C) += sum over i with nn[b,i]==r of gout[b,i,col0:col0+C].   */

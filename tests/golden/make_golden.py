@@ -143,11 +143,124 @@ def golden_ops(gcn3d):
     save("ops", **arrays)
 
 
+def _rf_recorder(gcn3d):
+    """Wrap the reference's get_receptive_fields to log the RF-F index tensors."""
+    log = []
+    orig = gcn3d.get_receptive_fields
+
+    def wrapped(neighbor_num, vertices, feature_map=None, mode='RF-F'):
+        d, i = orig(neighbor_num, vertices, feature_map=feature_map, mode=mode)
+        if mode == 'RF-F':
+            log.append(i.clone())
+        return d, i
+    gcn3d.get_receptive_fields = wrapped
+    return log, lambda: setattr(gcn3d, "get_receptive_fields", orig)
+
+
+def golden_e2e_eval(FLAGS, gcn3d):
+    """PoseNet9D built and run as evaluation/evaluate.py does (FLAGS.train=0 before
+    construction, .eval()), deterministic weights (oracle.synth.fill_params)."""
+    sys.path.insert(0, ROOT)
+    from oracle.synth import fill_params, synth_batch
+    from network.fs_net_repo.PoseNet9D import PoseNet9D
+    FLAGS.train = 0
+    arrays = {}
+    for k in (20, 16):
+        FLAGS.gcn_n_num = k
+        net = fill_params(PoseNet9D()).eval()
+        batch = synth_batch(2, 1028, seed=1, train=False)
+        log, undo = _rf_recorder(gcn3d)
+        torch.manual_seed(1234)
+        with torch.no_grad():
+            out = net(batch["PC"], batch["obj_id"])
+        undo()
+        torch.manual_seed(1234)
+        s1 = torch.randperm(1028)[:257]
+        s2 = torch.randperm(257)[:64]
+        names = ["p_green_R", "p_red_R", "f_green_R", "f_red_R", "Pred_T", "Pred_s"]
+        for n, t in zip(names, out[4:]):
+            arrays[f"k{k}_{n}"] = t
+        for i, r in enumerate(log):
+            arrays[f"k{k}_rf{i}"] = small_idx(r)
+        arrays[f"k{k}_sample1"] = small_idx(s1)
+        arrays[f"k{k}_sample2"] = small_idx(s2)
+        # backbone feature (concat) on a strided subset of points, via a forward hook
+        feats = []
+        h = net.face_recon.register_forward_hook(lambda m, i, o: feats.append(o[2]))
+        torch.manual_seed(1234)
+        with torch.no_grad():
+            net(batch["PC"], batch["obj_id"])
+        h.remove()
+        arrays[f"k{k}_feat_s16"] = feats[0][:, ::16, :].contiguous()
+    arrays["n_state_keys"] = np.int64(len(net.state_dict()))
+    FLAGS.gcn_n_num = 20
+    FLAGS.train = 1
+    save("e2e_eval", **arrays)
+
+
+def golden_e2e_train(FLAGS, gcn3d):
+    """HSPose('PoseNet_only') train-mode step as engine/train.py:76-107 runs it: forward with
+    do_loss=True, sum of all loss terms, backward.  Dropout p=0 and augmentation
+    probabilities 0 (device RNG streams differ between CPU and GPU)."""
+    sys.path.insert(0, ROOT)
+    from oracle.synth import fill_params, synth_batch
+    from network.HSPose import HSPose
+    FLAGS.train = 1
+    for n in ("aug_pc_pro", "aug_rt_pro", "aug_bb_pro", "aug_bc_pro"):
+        setattr(FLAGS, n, 0.0)
+    net = fill_params(HSPose("PoseNet_only")).train()
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    batch = synth_batch(4, 1028, seed=2, train=True)
+    log, undo = _rf_recorder(gcn3d)
+    torch.manual_seed(4321)
+    out, losses = net(**batch, do_loss=True)
+    undo()
+    arrays = {}
+    fs = {k: v.reshape(()) for k, v in losses["fsnet_loss"].items()}
+    total_fs = sum(fs.values())
+    for k, v in fs.items():
+        arrays["loss_fs_" + k] = v
+    for grp in ("recon_loss", "geo_loss", "prop_loss"):
+        for k, v in losses[grp].items():
+            arrays[f"loss_{grp}_{k}"] = v.reshape(())
+    total_fs.backward()
+    for i, r in enumerate(log):
+        arrays[f"rf{i}"] = small_idx(r)
+    for n in ("recon", "face_normal", "face_dis", "face_f"):
+        arrays["out_" + n] = out[n][:, ::64].contiguous()
+    for n in ("p_green_R", "p_red_R", "f_green_R", "f_red_R", "Pred_T", "Pred_s"):
+        arrays["out_" + n] = out[n]
+    gn = {}
+    for name, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        gn[name] = float(p.grad.norm())
+        if p.numel() <= 4096 or name.endswith("directions"):
+            arrays["grad::" + name] = p.grad
+    arrays["grad_norm_names"] = np.array(sorted(gn.keys()))
+    arrays["grad_norm_values"] = np.array([gn[k] for k in sorted(gn.keys())], dtype=np.float64)
+    # BN running stats after the step (momentum update) for two layers
+    sd = net.state_dict()
+    for n in ("posenet.face_recon.bn1.running_mean", "posenet.face_recon.bn1.running_var",
+              "posenet.rot_green.bn2.running_mean"):
+        arrays["post::" + n] = sd[n]
+    for n in ("aug_pc_pro", "aug_rt_pro", "aug_bb_pro", "aug_bc_pro"):
+        setattr(FLAGS, n, {"aug_pc_pro": 0.2}.get(n, 0.3))
+    save("e2e_train", **arrays)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    _args = sys.argv[1:]
     FLAGS, gcn3d = import_reference()
-    which = sys.argv[1:] or ["knn", "ops"]
+    which = _args or ["knn", "ops", "e2e_eval", "e2e_train"]
     if "knn" in which:
         golden_knn(gcn3d)
     if "ops" in which:
         golden_ops(gcn3d)
+    if "e2e_eval" in which:
+        golden_e2e_eval(FLAGS, gcn3d)
+    if "e2e_train" in which:
+        golden_e2e_train(FLAGS, gcn3d)

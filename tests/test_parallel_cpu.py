@@ -1,0 +1,81 @@
+"""CPU, gloo, world_size 2: the data-parallel host logic (hs-pose_b200/parallel.py)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from hspose_b200 import parallel
+    r, w, _ = parallel.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+    flat = parallel.FlatGradients(net.parameters())
+    g = torch.Generator().manual_seed(7)
+    batch = {"x": torch.randn(8, 6, generator=g), "y": torch.randn(8, 2, generator=g), "tag": "t"}
+    mine = parallel.shard_batch(batch, rank, world)
+    assert mine["x"].shape[0] == 4 and mine["tag"] == "t"
+    flat.zero()
+    torch.nn.functional.mse_loss(net(mine["x"]), mine["y"]).backward()
+    flat.all_reduce_mean()
+    # single-process gradient of the whole batch (equal shard sizes -> mean of shard grads)
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+    ref.load_state_dict(net.state_dict())
+    torch.nn.functional.mse_loss(ref(batch["x"]), batch["y"]).backward()
+    refflat = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+    ok = torch.allclose(flat.flat, refflat, atol=1e-6)
+    # views stay attached after zero()
+    flat.zero()
+    ok = ok and all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in net.parameters())
+    ok = ok and float(sum(p.grad.abs().sum() for p in net.parameters())) == 0.0
+    # same permutation on every rank after seed_all
+    parallel.seed_all(123)
+    perm = torch.randperm(1028)[:257]
+    gathered = [torch.empty_like(perm) for _ in range(world)]
+    dist.all_gather(gathered, perm)
+    ok = ok and all(torch.equal(gathered[0], t) for t in gathered)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_equals_big_batch():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret[0] and ret[1]
+
+
+def test_clip_matches_torch():
+    import sys
+    from hspose_b200 import parallel
+    net = torch.nn.Linear(10, 10)
+    flat = parallel.FlatGradients(net.parameters())
+    net(torch.ones(3, 10)).sum().backward()
+    ref = [p.grad.clone() for p in net.parameters()]
+    n1 = flat.clip_(0.5)
+    n2 = torch.nn.utils.clip_grad_norm_([torch.nn.Parameter(torch.zeros_like(r)) for r in ref], 0.5)
+    tot = torch.sqrt(sum((r ** 2).sum() for r in ref))
+    assert torch.allclose(n1, tot)
+    for p, r in zip(net.parameters(), ref):
+        assert torch.allclose(p.grad, r * min(1.0, 0.5 / (tot.item() + 1e-6)), atol=1e-6)
