@@ -110,11 +110,13 @@ def _alg_bytes(name, a, train=True):
     """ALGORITHMIC bytes of one launch (each kernel-boundary input read once, each output
     written once; fp32, int32 indices) — the per-kernel split of SURVEY.md §8(d)'s formula."""
     if name == "hsp_graph_conv_fwd":
-        B, N, k, S, C = a[:5]
-        return B * (12 * N + 4 * N * k + 4 * N * (S + 1) * C + 4 * N * C + (N * S * C if train else 0))
+        dt, B, N, k, S, C = a[:6]
+        e = 2 if dt == 1 else 4   # bytes per element of P
+        return B * (12 * N + 4 * N * k + e * N * (S + 1) * C + 4 * N * C + (N * S * C if train else 0))
     if name == "hsp_graph_conv_bwd":
-        B, N, k, S, C = a[:5]
-        return B * (12 * N + 4 * N * k + 4 * N * (S + 1) * C + N * S * C + 4 * N * C + 4 * N * (S + 1) * C)
+        dt, B, N, k, S, C = a[:6]
+        e = 2 if dt == 1 else 4
+        return B * (12 * N + 4 * N * k + e * N * (S + 1) * C + N * S * C + 4 * N * C + 4 * N * (S + 1) * C)
     if name == "hsp_surface_conv_fwd" or name == "hsp_surface_conv_bwd":
         B, N, k, S, C = a[:5]
         return B * (12 * N + 4 * N * k + 4 * N * C)
@@ -142,7 +144,7 @@ def _alg_bytes(name, a, train=True):
 def kernel_breakdown(records, steps):
     agg = {}
     for name, a, ms in records:
-        key = (name, a[:6])
+        key = (name, a[:7])
         d = agg.setdefault(key, {"ms": 0.0, "n": 0})
         d["ms"] += ms
         d["n"] += 1

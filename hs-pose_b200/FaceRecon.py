@@ -17,29 +17,66 @@ from . import gcn3d, ops
 from .flags import FLAGS
 
 
-def bn_points(bn: nn.BatchNorm1d, x_bnc):
-    """nn.BatchNorm1d over the channel axis of a (bs, N, C) tensor — the same
-    statistics as bn(x.transpose(1, 2)).transpose(1, 2) (FaceRecon.py:90-95)."""
-    B, N, C = x_bnc.shape
-    return bn(x_bnc.reshape(B * N, C)).view(B, N, C)
+FEAT_LD = 1296   # 1286 feature channels + 3 centred xyz + 7 zeros: 16-element aligned rows
 
 
-def conv1x1(conv: nn.Conv1d, x_bnc):
-    """nn.Conv1d(kernel_size=1) applied in (bs, N, C) layout."""
-    return F.linear(x_bnc, conv.weight[:, :, 0], conv.bias)
+def mixed_precision():
+    """The fast dense path is active inside torch.autocast('cuda', bf16): bf16 activations in
+    16-byte aligned (M,C) matrices for the tensor-core GEMMs, fused BN+ReLU kernels (K6b)."""
+    return torch.is_autocast_enabled("cuda")
+
+
+def bn_points(bn: nn.BatchNorm1d, x_bnc, relu=False):
+    """nn.BatchNorm1d over the channel axis of a (bs, N, C) / (M, C) tensor — the same
+    statistics as bn(x.transpose(1, 2)).transpose(1, 2) (FaceRecon.py:90-95) — optionally
+    fused with the ReLU that follows it everywhere in the reference."""
+    shape = x_bnc.shape
+    x2 = x_bnc.reshape(-1, shape[-1])
+    if bn.training and mixed_precision() and x2.is_cuda and shape[-1] % 8 == 0 and x2.shape[0] > 1:
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        y = ops.bn_relu(x2, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
+                        bn.momentum, relu)
+    else:
+        y = bn(x2)
+        if relu:
+            y = F.relu(y)
+    return y.view(shape)
+
+
+def conv1x1(conv: nn.Conv1d, x_bnc, pad_in=0, pad_out=0):
+    """nn.Conv1d(kernel_size=1) applied in (bs, N, C) layout.  pad_in / pad_out append
+    zero input columns / output rows to the weight so GEMM dims stay 16-byte aligned."""
+    w, b = conv.weight[:, :, 0], conv.bias
+    if pad_in or pad_out:
+        w = F.pad(w, (0, pad_in, 0, pad_out))
+        if b is not None and pad_out:
+            b = F.pad(b, (0, pad_out))
+    return F.linear(x_bnc, w, b)
 
 
 def seq_points(seq: nn.Sequential, x_bnc):
-    """Run a Conv1d/BatchNorm1d/ReLU nn.Sequential (FaceRecon.py:38-68) in (bs, N, C) layout."""
-    for m in seq:
+    """Run a Conv1d/BatchNorm1d/ReLU nn.Sequential (FaceRecon.py:38-68) in (bs, N, C) layout;
+    BN+ReLU pairs are fused; a narrow last conv (3 / 30 channels) is computed 8-aligned."""
+    mods = list(seq)   # an nn.Sequential or a plain list of its modules
+    i = 0
+    while i < len(mods):
+        m = mods[i]
         if isinstance(m, nn.Conv1d):
-            x_bnc = conv1x1(m, x_bnc)
+            pad_in = x_bnc.shape[-1] - m.in_channels
+            pad_out = (-m.out_channels) % 8 if mixed_precision() else 0
+            x_bnc = conv1x1(m, x_bnc, pad_in, pad_out)
+            if pad_out:
+                x_bnc = x_bnc[..., :m.out_channels]
         elif isinstance(m, nn.BatchNorm1d):
-            x_bnc = bn_points(m, x_bnc)
+            fuse = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+            x_bnc = bn_points(m, x_bnc, relu=fuse)
+            i += 1 if fuse else 0
         elif isinstance(m, nn.ReLU):
             x_bnc = F.relu(x_bnc)
         else:
             raise NotImplementedError(type(m))
+        i += 1
     return x_bnc
 
 
@@ -96,11 +133,11 @@ class FaceRecon(nn.Module):
         vertices = vertices.contiguous()
         with gcn3d.neighbor_cache():
             fm_0 = F.relu(self.conv_0(vertices, k))
-            fm_1 = F.relu(bn_points(self.bn1, self.conv_1(vertices, fm_0, k)))
+            fm_1 = bn_points(self.bn1, self.conv_1(vertices, fm_0, k), relu=True)
             v_pool_1, fm_pool_1 = self.pool_1(vertices, fm_1)
             k1 = min(k, v_pool_1.shape[1] // 8)
-            fm_2 = F.relu(bn_points(self.bn2, self.conv_2(v_pool_1, fm_pool_1, k1)))
-            fm_3 = F.relu(bn_points(self.bn3, self.conv_3(v_pool_1, fm_2, k1)))
+            fm_2 = bn_points(self.bn2, self.conv_2(v_pool_1, fm_pool_1, k1), relu=True)
+            fm_3 = bn_points(self.bn3, self.conv_3(v_pool_1, fm_2, k1), relu=True)
             v_pool_2, fm_pool_2 = self.pool_2(v_pool_1, fm_3)
             fm_4 = self.conv_4(v_pool_2, fm_pool_2, min(k, v_pool_2.shape[1] // 8))
         f_global = fm_4.max(1)[0]  # (bs, 512)
@@ -108,16 +145,42 @@ class FaceRecon(nn.Module):
         # nearest up-sampling (FaceRecon.py:100-104) fused with the concat (:107)
         nearest_pool_1 = ops.knn3(vertices, v_pool_1, 1, drop_first=0, formula=ops.DIST_NEAREST)[1]
         nearest_pool_2 = ops.knn3(vertices, v_pool_2, 1, drop_first=0, formula=ops.DIST_NEAREST)[1]
-        feat = ops.concat_upsample(
-            [fm_0, fm_1, fm_2, fm_3, fm_4, one_hot],
-            [None, None, nearest_pool_1[..., 0], nearest_pool_1[..., 0], nearest_pool_2[..., 0], "bcast"],
-            vertice_num)
+        pieces = [fm_0, fm_1, fm_2, fm_3, fm_4, one_hot]
+        nns = [None, None, nearest_pool_1[..., 0], nearest_pool_1[..., 0], nearest_pool_2[..., 0], "bcast"]
+        mixed = mixed_precision()
+        if mixed:
+            # bf16, rows padded to FEAT_LD; columns 1286:1289 carry the centred xyz so the same
+            # buffer is PoseNet9D's `feat_for_ts` (PoseNet9D.py:47) — no second concat
+            feat_pad = ops.concat_upsample(pieces + [vertices], nns + [None], vertice_num,
+                                           ld=FEAT_LD, out_dtype=torch.bfloat16)
+            feat = feat_pad[:, :, :feat_pad.shape[2] - (FEAT_LD - 1286)]
+            self.feat_padded = feat_pad
+        else:
+            feat = ops.concat_upsample(pieces, nns, vertice_num)
+            self.feat_padded = None
 
         if FLAGS.train:
-            conv1d_out = seq_points(self.conv1d_block, feat)           # (bs, N, 256)
-            recon = seq_points(self.recon_head, conv1d_out)            # (bs, N, 3)
-            feat_face_in = torch.cat(
-                [f_global.unsqueeze(1).expand(-1, vertice_num, -1), conv1d_out, vertices], dim=2)
-            face = seq_points(self.face_head, feat_face_in)            # (bs, N, 30)
+            conv1d_out = seq_points(self.conv1d_block, feat_pad if mixed else feat)   # (bs, N, 256)
+            recon = seq_points(self.recon_head, conv1d_out)                            # (bs, N, 3)
+            face = self._face_head(f_global, conv1d_out, vertices)                     # (bs, N, 30)
             return recon, face, feat
         return None, None, feat
+
+    def _face_head(self, f_global, conv1d_out, vertices):
+        """face_head on cat[f_global repeated, conv1d_out, xyz] (FaceRecon.py:118-124).  The
+        f_global block of the first conv is a per-object constant: W[:, :512] @ f_global[b]
+        is computed once per object and broadcast instead of multiplying N identical rows."""
+        bs, n, _ = conv1d_out.shape
+        if not mixed_precision():
+            x = torch.cat([f_global.unsqueeze(1).expand(-1, n, -1), conv1d_out, vertices], dim=2)
+            return seq_points(self.face_head, x)
+        conv0 = self.face_head[0]
+        w = conv0.weight[:, :, 0]
+        cg = f_global.shape[1]
+        per_obj = F.linear(f_global, w[:, :cg], conv0.bias)                     # (bs, 512)
+        tail = torch.cat([conv1d_out, vertices.to(conv1d_out.dtype)], dim=2)     # (bs, N, 259)
+        pad = (-tail.shape[2]) % 8
+        tail = F.pad(tail, (0, pad))
+        x = torch.baddbmm(per_obj.unsqueeze(1), tail,
+                          F.pad(w[:, cg:], (0, pad)).t().unsqueeze(0).expand(bs, -1, -1))
+        return seq_points(list(self.face_head)[1:], x)

@@ -27,22 +27,25 @@ class PoseNet9D(nn.Module):
         recon, face, feat = self.face_recon(centred, obj_id)
 
         if FLAGS.train:
-            recon = recon + mean
+            recon, face = recon.float() + mean, face.float()
             face_normal = face[:, :, :18].view(bs, p_num, 6, 3)
             face_normal = face_normal / torch.norm(face_normal, dim=-1, keepdim=True)
             face_dis = face[:, :, 18:24]
             face_f = torch.sigmoid(face[:, :, 24:])
         else:
             face_normal, face_dis, face_f, recon = [None] * 4
-        green_R_vec = self.rot_green.forward_points(feat)   # b x 4
-        red_R_vec = self.rot_red.forward_points(feat)       # b x 4
+        # mixed precision: one bf16 buffer (bs, N, 1296) = [feat | centred xyz | 0] feeds all heads
+        feat_pad = self.face_recon.feat_padded
+        head_in = feat if feat_pad is None else feat_pad
+        green_R_vec = self.rot_green.forward_points(head_in).float()   # b x 4
+        red_R_vec = self.rot_red.forward_points(head_in).float()       # b x 4
         p_green_R = green_R_vec[:, 1:] / (torch.norm(green_R_vec[:, 1:], dim=1, keepdim=True) + 1e-6)
         p_red_R = red_R_vec[:, 1:] / (torch.norm(red_R_vec[:, 1:], dim=1, keepdim=True) + 1e-6)
         f_green_R = torch.sigmoid(green_R_vec[:, 0])
         f_red_R = torch.sigmoid(red_R_vec[:, 0])
 
-        feat_for_ts = torch.cat([feat, centred], dim=2)
+        feat_for_ts = torch.cat([feat, centred], dim=2) if feat_pad is None else feat_pad
         T, s = self.ts.forward_points(feat_for_ts)
-        Pred_T = T + mean[:, 0, :]
-        Pred_s = s
+        Pred_T = T.float() + mean[:, 0, :]
+        Pred_s = s.float()
         return recon, face_normal, face_dis, face_f, p_green_R, p_red_R, f_green_R, f_red_R, Pred_T, Pred_s

@@ -28,8 +28,9 @@ class _PointHead(nn.Module):
         self.bn3 = nn.BatchNorm1d(256)
 
     def forward_points(self, x_bnc):
-        x = F.relu(bn_points(self.bn1, conv1x1(self.conv1, x_bnc)))
-        x = F.relu(bn_points(self.bn2, conv1x1(self.conv2, x)))
+        # x_bnc may be the 16-aligned padded feature buffer (extra columns get zero weights)
+        x = bn_points(self.bn1, conv1x1(self.conv1, x_bnc, pad_in=x_bnc.shape[-1] - self.f), relu=True)
+        x = bn_points(self.bn2, conv1x1(self.conv2, x), relu=True)
         x = torch.max(x, 1)[0]                                  # (bs, 256): max over points
         x = F.relu(self.bn3(F.linear(x, self.conv3.weight[:, :, 0], self.conv3.bias)))
         x = self.drop1(x)

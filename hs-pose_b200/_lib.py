@@ -21,17 +21,22 @@ SIGNATURES = {
     "hsp_surface_conv_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
     "hsp_surface_conv_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P,
                                      c_size_t, P]),
-    "hsp_graph_conv_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "hsp_graph_conv_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "hsp_graph_conv_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
-    "hsp_graph_conv_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P,
+    "hsp_graph_conv_bwd": (c_int, [P, P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P, P,
                                    P, c_size_t, P]),
     "hsp_gather_max_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "hsp_gather_max_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "hsp_orl_global_workspace_bytes": (c_size_t, [c_int] * 3),
     "hsp_orl_global_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P, c_size_t, P]),
     "hsp_orl_global_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P]),
-    "hsp_upsample_rows_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P, c_int, c_int, P]),
-    "hsp_upsample_rows_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "hsp_upsample_rows_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P]),
+    "hsp_upsample_rows_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "hsp_bn_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "hsp_bn_relu_fwd": (c_int, [P, c_int, c_int, c_int, c_int, P, P, ctypes.c_float, ctypes.c_float,
+                                c_int, P, P, P, P, P, P, c_int, P, c_size_t, P]),
+    "hsp_bn_relu_bwd": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, P, P, P, P, c_int, P, P, P,
+                                c_int, P, c_size_t, P]),
     "hsp_chamfer_fwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P, P]),
     "hsp_chamfer_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, P]),
 }

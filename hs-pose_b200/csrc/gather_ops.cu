@@ -5,6 +5,8 @@
 // indexing_neighbor_new (gcn3d.py:39-47) never materialises (B,N,k,C): one
 // thread owns one channel, a warp reads 128 contiguous bytes of each gathered
 // row, the max over neighbours stays in a register.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace hsp {
@@ -100,27 +102,42 @@ orl_bwd_kernel(const float* __restrict__ gG, const int32_t* __restrict__ idx,
   }
 }
 
+template <typename TO> __device__ __forceinline__ TO from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename TO>
 __global__ void __launch_bounds__(GO_THREADS)
 upsample_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ nn, int Nsrc,
-                    int M, int C, float* __restrict__ out, int ldo, int col0) {
+                    int M, int C, TO* __restrict__ out, int ldo, int col0) {
   const int b = blockIdx.y;
   const int i_end = min((int)(blockIdx.x + 1) * GO_PT, M);
   for (int i = blockIdx.x * GO_PT; i < i_end; ++i) {
     const int r = nn ? __ldg(nn + (size_t)b * M + i) : (Nsrc == 1 ? 0 : i);
     const float* src = feat + ((size_t)b * Nsrc + r) * C;
-    float* dst = out + ((size_t)b * M + i) * ldo + col0;
-    for (int c = threadIdx.x; c < C; c += GO_THREADS) dst[c] = __ldg(src + c);
+    TO* dst = out + ((size_t)b * M + i) * ldo + col0;
+    for (int c = threadIdx.x; c < C; c += GO_THREADS) dst[c] = from_f32<TO>(__ldg(src + c));
   }
 }
+// nn != NULL: scatter-add (float atomics; a source row is hit by ~4 points).
+// nn == NULL (identity): plain converting copy of the column slice.
+template <typename TO>
 __global__ void __launch_bounds__(GO_THREADS)
-upsample_bwd_kernel(const float* __restrict__ gout, const int32_t* __restrict__ nn, int Nsrc,
+upsample_bwd_kernel(const TO* __restrict__ gout, const int32_t* __restrict__ nn, int Nsrc,
                     int M, int C, int ldo, int col0, float* __restrict__ gfeat) {
   const int b = blockIdx.y;
   const int i_end = min((int)(blockIdx.x + 1) * GO_PT, M);
   for (int i = blockIdx.x * GO_PT; i < i_end; ++i) {
-    float* dst = gfeat + ((size_t)b * Nsrc + __ldg(nn + (size_t)b * M + i)) * C;
-    const float* src = gout + ((size_t)b * M + i) * ldo + col0;
-    for (int c = threadIdx.x; c < C; c += GO_THREADS) atomicAdd(dst + c, src[c]);
+    const TO* src = gout + ((size_t)b * M + i) * ldo + col0;
+    if (nn) {
+      float* dst = gfeat + ((size_t)b * Nsrc + __ldg(nn + (size_t)b * M + i)) * C;
+      for (int c = threadIdx.x; c < C; c += GO_THREADS) atomicAdd(dst + c, to_f32(src[c]));
+    } else {
+      float* dst = gfeat + ((size_t)b * Nsrc + i) * C;
+      for (int c = threadIdx.x; c < C; c += GO_THREADS) dst[c] = to_f32(src[c]);
+    }
   }
 }
 
@@ -199,32 +216,43 @@ extern "C" int hsp_orl_global_bwd(const float* gG, const int32_t* idx, const uin
 }
 
 extern "C" int hsp_upsample_rows_fwd(const float* feat, const int32_t* nn, int B, int Nsrc,
-                                     int M, int C, float* out, int ldo, int col0,
+                                     int M, int C, void* out, int ldo, int col0, int out_dtype,
                                      void* stream) {
   using namespace hsp;
   if (!feat || !out || B < 0 || Nsrc <= 0 || M < 0 || C <= 0 || col0 < 0 ||
       col0 + C > ldo || B > 65535)
     return HSP_EINVAL;
   if (!nn && Nsrc != 1 && Nsrc != M) return HSP_EINVAL;  /* identity / broadcast modes */
+  if (out_dtype != HSP_DTYPE_F32 && out_dtype != HSP_DTYPE_BF16) return HSP_EINVAL;
   if (B == 0 || M == 0) return HSP_OK;
   dim3 grid((M + GO_PT - 1) / GO_PT, B);
-  upsample_fwd_kernel<<<grid, GO_THREADS, 0, (cudaStream_t)stream>>>(feat, nn, Nsrc, M, C, out,
-                                                                     ldo, col0);
+  if (out_dtype == HSP_DTYPE_BF16)
+    upsample_fwd_kernel<__nv_bfloat16><<<grid, GO_THREADS, 0, (cudaStream_t)stream>>>(
+        feat, nn, Nsrc, M, C, (__nv_bfloat16*)out, ldo, col0);
+  else
+    upsample_fwd_kernel<float><<<grid, GO_THREADS, 0, (cudaStream_t)stream>>>(
+        feat, nn, Nsrc, M, C, (float*)out, ldo, col0);
   HSP_LAUNCH_CHECK();
   return HSP_OK;
 }
 
-extern "C" int hsp_upsample_rows_bwd(const float* gout, const int32_t* nn, int B, int Nsrc,
-                                     int M, int C, int ldo, int col0, float* gfeat,
-                                     void* stream) {
+extern "C" int hsp_upsample_rows_bwd(const void* gout, const int32_t* nn, int B, int Nsrc,
+                                     int M, int C, int ldo, int col0, int gout_dtype,
+                                     float* gfeat, void* stream) {
   using namespace hsp;
-  if (!gout || !nn || !gfeat || B < 0 || Nsrc <= 0 || M < 0 || C <= 0 || col0 < 0 ||
+  if (!gout || !gfeat || B < 0 || Nsrc <= 0 || M < 0 || C <= 0 || col0 < 0 ||
       col0 + C > ldo || B > 65535)
     return HSP_EINVAL;
+  if (!nn && Nsrc != M) return HSP_EINVAL;
+  if (gout_dtype != HSP_DTYPE_F32 && gout_dtype != HSP_DTYPE_BF16) return HSP_EINVAL;
   if (B == 0 || M == 0) return HSP_OK;
   dim3 grid((M + GO_PT - 1) / GO_PT, B);
-  upsample_bwd_kernel<<<grid, GO_THREADS, 0, (cudaStream_t)stream>>>(gout, nn, Nsrc, M, C, ldo,
-                                                                     col0, gfeat);
+  if (gout_dtype == HSP_DTYPE_BF16)
+    upsample_bwd_kernel<__nv_bfloat16><<<grid, GO_THREADS, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)gout, nn, Nsrc, M, C, ldo, col0, gfeat);
+  else
+    upsample_bwd_kernel<float><<<grid, GO_THREADS, 0, (cudaStream_t)stream>>>(
+        (const float*)gout, nn, Nsrc, M, C, ldo, col0, gfeat);
   HSP_LAUNCH_CHECK();
   return HSP_OK;
 }

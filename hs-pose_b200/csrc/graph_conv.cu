@@ -12,6 +12,8 @@
 // reads 128 contiguous bytes per (neighbour, support)).  Unit directions of
 // the tile's (point, neighbour) pairs are computed once per CTA into shared
 // memory and broadcast.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace hsp {
@@ -19,6 +21,11 @@ namespace hsp {
 constexpr int GC_THREADS = 128;  // channels per CTA slice
 constexpr int GC_PT = 8;         // points per CTA tile
 constexpr int GC_MAXK = 64;
+
+__device__ __forceinline__ float ld_p(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_p(const __nv_bfloat16* p) {
+  return __bfloat162float(__ldg(p));
+}
 
 // F.normalize(nbr - centre, dim=-1): x / max(||x||_2, 1e-12)   (gcn3d.py:53-55)
 __device__ __forceinline__ void unit_dir(const float* __restrict__ xb, int i, int j, float* r) {
@@ -89,10 +96,10 @@ surface_conv_fwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict
   }
 }
 
-template <int S>
+template <int S, typename TP>
 __global__ void __launch_bounds__(GC_THREADS)
 graph_conv_fwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
-                      const float* __restrict__ dirn, const float* __restrict__ P, int N, int k,
+                      const float* __restrict__ dirn, const TP* __restrict__ P, int N, int k,
                       int C, float* __restrict__ out, uint8_t* __restrict__ argmax) {
   __shared__ int s_idx[GC_PT * GC_MAXK];
   __shared__ float s_r[GC_PT * GC_MAXK * 3];
@@ -112,7 +119,7 @@ graph_conv_fwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__
   }
   __syncthreads();
   if (c >= C) return;
-  const float* Pb = P + (size_t)b * N * LD;
+  const TP* Pb = P + (size_t)b * N * LD;
   for (int p = 0; p < npts; ++p) {
     float acc[S];
     int am[S];
@@ -120,10 +127,10 @@ graph_conv_fwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__
     for (int s = 0; s < S; ++s) { acc[s] = -INFINITY; am[s] = 0; }
 #pragma unroll 2
     for (int n = 0; n < k; ++n) {
-      const float* sup = Pb + (size_t)s_idx[p * k + n] * LD + C + c;
+      const TP* sup = Pb + (size_t)s_idx[p * k + n] * LD + C + c;
       float v[S];
 #pragma unroll
-      for (int s = 0; s < S; ++s) v[s] = __ldg(sup + s * C);
+      for (int s = 0; s < S; ++s) v[s] = ld_p(sup + s * C);
       const float rx = s_r[3 * (p * k + n)], ry = s_r[3 * (p * k + n) + 1],
                   rz = s_r[3 * (p * k + n) + 2];
 #pragma unroll
@@ -137,7 +144,7 @@ graph_conv_fwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__
 #pragma unroll
     for (int s = 0; s < S; ++s) sum += acc[s];
     const size_t row = (size_t)b * N + i0 + p;
-    out[row * C + c] = Pb[(size_t)(i0 + p) * LD + c] + __fdiv_rn(sum, (float)S);
+    out[row * C + c] = ld_p(Pb + (size_t)(i0 + p) * LD + c) + __fdiv_rn(sum, (float)S);
     if (argmax) {
 #pragma unroll
       for (int s = 0; s < S; ++s) argmax[row * SC + s * C + c] = (uint8_t)am[s];
@@ -251,10 +258,10 @@ __global__ void dir_reduce_kernel(const float* __restrict__ partial, int rows, i
   out[j] = s;
 }
 
-template <int S>
+template <int S, typename TP>
 __global__ void __launch_bounds__(GC_THREADS)
 graph_conv_bwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
-                      const float* __restrict__ dirn, const float* __restrict__ P,
+                      const float* __restrict__ dirn, const TP* __restrict__ P,
                       const uint8_t* __restrict__ argmax, const float* __restrict__ gout, int B,
                       int N, int k, int C, float* __restrict__ gP, float* __restrict__ partial) {
   __shared__ int s_idx[GC_PT * GC_MAXK];
@@ -280,7 +287,7 @@ graph_conv_bwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__
     stage_tile(xyz + (size_t)b * N * 3, idx + (size_t)b * N * k, i0, npts, k, s_idx, s_r);
     __syncthreads();
     if (c < C) {
-      const float* Pb = P + (size_t)b * N * LD;
+      const TP* Pb = P + (size_t)b * N * LD;
       float* gPb = gP + (size_t)b * N * LD;
       for (int p = 0; p < npts; ++p) {
         const size_t row = (size_t)b * N + i0 + p;
@@ -295,7 +302,7 @@ graph_conv_bwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__
           const float th = fmaxf(fmaf(r[2], dz[s], fmaf(r[1], dy[s], r[0] * dx[s])), 0.0f);
           if (th > 0.0f) {
             atomicAdd(gPb + off, gs * th);
-            const float gv = gs * __ldg(Pb + off);
+            const float gv = gs * ld_p(Pb + off);
             gx[s] = fmaf(gv, r[0], gx[s]);
             gy[s] = fmaf(gv, r[1], gy[s]);
             gz[s] = fmaf(gv, r[2], gz[s]);
@@ -353,15 +360,22 @@ extern "C" int hsp_surface_conv_fwd(const float* xyz, const int32_t* idx, const 
 }
 
 extern "C" int hsp_graph_conv_fwd(const float* xyz, const int32_t* idx, const float* dirn,
-                                  const float* P, int B, int N, int k, int S, int C,
+                                  const void* P, int p_dtype, int B, int N, int k, int S, int C,
                                   float* out, uint8_t* argmax, void* stream) {
   using namespace hsp;
   if (!xyz || !idx || !dirn || !P || !out || bad_dims(B, N, k, S, C)) return HSP_EINVAL;
   if (argmax && k > 255) return HSP_EINVAL;
+  if (p_dtype != HSP_DTYPE_F32 && p_dtype != HSP_DTYPE_BF16) return HSP_EINVAL;
   if (B == 0) return HSP_OK;
   dim3 grid((N + GC_PT - 1) / GC_PT, B, (C + GC_THREADS - 1) / GC_THREADS);
   cudaStream_t st = (cudaStream_t)stream;
-  HSP_DISPATCH_S(S, (graph_conv_fwd_kernel<S><<<grid, GC_THREADS, 0, st>>>(xyz, idx, dirn, P, N, k, C, out, argmax)));
+  if (p_dtype == HSP_DTYPE_BF16) {
+    HSP_DISPATCH_S(S, (graph_conv_fwd_kernel<S, __nv_bfloat16><<<grid, GC_THREADS, 0, st>>>(
+                          xyz, idx, dirn, (const __nv_bfloat16*)P, N, k, C, out, argmax)));
+  } else {
+    HSP_DISPATCH_S(S, (graph_conv_fwd_kernel<S, float><<<grid, GC_THREADS, 0, st>>>(
+                          xyz, idx, dirn, (const float*)P, N, k, C, out, argmax)));
+  }
   HSP_LAUNCH_CHECK();
   return HSP_OK;
 }
@@ -400,9 +414,10 @@ extern "C" int hsp_surface_conv_bwd(const float* xyz, const int32_t* idx, const 
 }
 
 extern "C" int hsp_graph_conv_bwd(const float* xyz, const int32_t* idx, const float* dirn,
-                                  const float* P, const uint8_t* argmax, const float* gout,
-                                  int B, int N, int k, int S, int C, float* gP, float* gdirn,
-                                  void* workspace, size_t workspace_bytes, void* stream) {
+                                  const void* P, int p_dtype, const uint8_t* argmax,
+                                  const float* gout, int B, int N, int k, int S, int C, float* gP,
+                                  float* gdirn, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
   using namespace hsp;
   if (!xyz || !idx || !dirn || !P || !argmax || !gout || !gP || !gdirn ||
       bad_dims(B, N, k, S, C))
@@ -418,8 +433,17 @@ extern "C" int hsp_graph_conv_bwd(const float* xyz, const int32_t* idx, const fl
     return HSP_ELAUNCH;
   const int ctas = bwd_ctas(B, N);
   dim3 grid(ctas, 1, (C + GC_THREADS - 1) / GC_THREADS);
-  HSP_DISPATCH_S(S, (graph_conv_bwd_kernel<S><<<grid, GC_THREADS, 0, st>>>(
-                        xyz, idx, dirn, P, argmax, gout, B, N, k, C, gP, (float*)workspace)));
+  if (p_dtype == HSP_DTYPE_BF16) {
+    HSP_DISPATCH_S(S, (graph_conv_bwd_kernel<S, __nv_bfloat16><<<grid, GC_THREADS, 0, st>>>(
+                          xyz, idx, dirn, (const __nv_bfloat16*)P, argmax, gout, B, N, k, C, gP,
+                          (float*)workspace)));
+  } else if (p_dtype == HSP_DTYPE_F32) {
+    HSP_DISPATCH_S(S, (graph_conv_bwd_kernel<S, float><<<grid, GC_THREADS, 0, st>>>(
+                          xyz, idx, dirn, (const float*)P, argmax, gout, B, N, k, C, gP,
+                          (float*)workspace)));
+  } else {
+    return HSP_EINVAL;
+  }
   HSP_LAUNCH_CHECK();
   const int cols = 3 * S * C;
   dir_reduce_kernel<<<(cols + 127) / 128, 128, 0, st>>>((const float*)workspace, ctas, cols, gdirn);

@@ -164,7 +164,8 @@ class HSlayer_surface(nn.Module):
         self.directions.data.uniform_(-stdv, stdv)
 
     def forward(self, vertices: "(bs, vertice_num, 3)", neighbor_num: 'int'):
-        f_STE = F.linear(vertices, self.STE_layer.weight[:, :, 0])
+        with torch.autocast("cuda", enabled=False):   # K = 3: keep the coordinates in fp32
+            f_STE = F.linear(vertices.float(), self.STE_layer.weight[:, :, 0])
         feature = self.graph_conv(None, vertices, neighbor_num)
         feature = self.ORL_forward(feature, vertices, neighbor_num)
         return feature + f_STE
@@ -217,6 +218,10 @@ class HS_layer(nn.Module):
         support rows, theta, the product, max over neighbours, mean over supports and the
         centre term are one kernel."""
         idx32 = neighbor_index if neighbor_index.dtype == torch.int32 else neighbor_index.to(torch.int32)
+        if torch.is_autocast_enabled("cuda"):
+            # mixed precision: bf16 P straight from the tensor-core GEMM into the gather kernel
+            return ops.hs_conv_mixed(vertices, idx32, F.normalize(self.directions, dim=0), feature_map,
+                                     self.weights, self.bias, self.support_num, self.out_channel)
         P = torch.addmm(self.bias, feature_map.reshape(-1, self.in_channel), self.weights)
         P = P.view(feature_map.shape[0], feature_map.shape[1], -1)
         dirn = F.normalize(self.directions, dim=0)

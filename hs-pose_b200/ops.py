@@ -12,12 +12,14 @@ from . import _lib
 
 DIST_NEIGHBOR = 0
 DIST_NEAREST = 1
+F32, BF16 = 0, 1   # HSP_DTYPE_*
 
 _launches = 0  # number of CUDA kernels launched through the C ABI (bench.py reads this)
 
 # kernels launched per entry point (memsets not counted)
 _KERNELS_PER_CALL = {"hsp_knn_feat": 2, "hsp_surface_conv_bwd": 2, "hsp_graph_conv_bwd": 2,
-                     "hsp_orl_global_fwd": 2, "hsp_chamfer_fwd": 2, "hsp_chamfer_bwd": 2}
+                     "hsp_orl_global_fwd": 2, "hsp_chamfer_fwd": 2, "hsp_chamfer_bwd": 2,
+                     "hsp_bn_relu_fwd": 3, "hsp_bn_relu_bwd": 3}
 
 _timing = None  # when a list: (name, int-args, start_event, end_event) per call
 
@@ -156,6 +158,32 @@ def surface_conv(xyz, idx32, dirn, S, C):
     return _SurfaceConv.apply(xyz, idx32, dirn, S, C)
 
 
+def _graph_conv_fwd_raw(xyz, idx32, dirn, P, S, C, want_argmax):
+    B, N, k = idx32.shape
+    if P.shape != (B, N, (S + 1) * C):
+        raise ValueError(f"P must be (B,N,(S+1)*C), got {tuple(P.shape)}")
+    dt = BF16 if P.dtype == torch.bfloat16 else F32
+    with torch.cuda.device(xyz.device):
+        out = torch.empty(B, N, C, dtype=torch.float32, device=xyz.device)
+        am = torch.empty(B, N, S * C, dtype=torch.uint8, device=xyz.device) if want_argmax else None
+        _call("hsp_graph_conv_fwd", _p(xyz), _p(idx32), _p(dirn), _p(P), dt, B, N, k, S, C,
+              _p(out), _p(am), _stream())
+    return out, am
+
+
+def _graph_conv_bwd_raw(xyz, idx32, dirn, P, am, gout, S, C):
+    B, N, k = idx32.shape
+    dt = BF16 if P.dtype == torch.bfloat16 else F32
+    with torch.cuda.device(xyz.device):
+        lib = _lib.load()
+        ws = _workspace(lib.hsp_graph_conv_bwd_workspace_bytes(B, N, k, S, C), xyz.device)
+        gP = torch.empty(B, N, (S + 1) * C, dtype=torch.float32, device=xyz.device)
+        gdirn = torch.empty_like(dirn)
+        _call("hsp_graph_conv_bwd", _p(xyz), _p(idx32), _p(dirn), _p(P), dt, _p(am), _p(gout),
+              B, N, k, S, C, _p(gP), _p(gdirn), _p(ws), ws.numel(), _stream())
+    return gP, gdirn
+
+
 class _GraphConv(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
@@ -164,39 +192,74 @@ class _GraphConv(torch.autograd.Function):
         idx32 = _need(idx32, torch.int32, "idx")
         dirn = _need(dirn, torch.float32, "dirn")
         P = _need(P, torch.float32, "P")
-        B, N, k = idx32.shape
-        if P.shape != (B, N, (S + 1) * C):
-            raise ValueError(f"P must be (B,N,(S+1)*C), got {tuple(P.shape)}")
         need_grad = any(ctx.needs_input_grad)
-        with torch.cuda.device(xyz.device):
-            out = torch.empty(B, N, C, dtype=torch.float32, device=xyz.device)
-            am = torch.empty(B, N, S * C, dtype=torch.uint8, device=xyz.device) if need_grad else None
-            _call("hsp_graph_conv_fwd", _p(xyz), _p(idx32), _p(dirn), _p(P), B, N, k, S, C,
-                  _p(out), _p(am), _stream())
+        out, am = _graph_conv_fwd_raw(xyz, idx32, dirn, P, S, C, need_grad)
         if need_grad:
             ctx.save_for_backward(xyz, idx32, dirn, P, am)
-        ctx.dims = (B, N, k, S, C)
+        ctx.dims = (S, C)
         return out
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gout):
         xyz, idx32, dirn, P, am = ctx.saved_tensors
-        B, N, k, S, C = ctx.dims
+        S, C = ctx.dims
         gout = _need(gout.float(), torch.float32, "gout")
-        with torch.cuda.device(xyz.device):
-            lib = _lib.load()
-            ws = _workspace(lib.hsp_graph_conv_bwd_workspace_bytes(B, N, k, S, C), xyz.device)
-            gP = torch.empty_like(P)
-            gdirn = torch.empty_like(dirn)
-            _call("hsp_graph_conv_bwd", _p(xyz), _p(idx32), _p(dirn), _p(P), _p(am), _p(gout),
-                  B, N, k, S, C, _p(gP), _p(gdirn), _p(ws), ws.numel(), _stream())
+        gP, gdirn = _graph_conv_bwd_raw(xyz, idx32, dirn, P, am, gout, S, C)
         return None, None, gdirn, gP, None, None
 
 
 def graph_conv(xyz, idx32, dirn, P, S, C):
     """K4: out = P[..., :C] + mean_s max_n(relu(rhat . dirn) * P[idx, C + s*C + c])."""
     return _GraphConv.apply(xyz, idx32, dirn, P, S, C)
+
+
+class _HSConvMixed(torch.autograd.Function):
+    """Mixed-precision HS graph convolution: P = fm @ W + b is produced in bf16 by a
+    tensor-core GEMM and consumed in bf16 by the fused gather kernel (half the gather
+    traffic, no fp32 copy of P); the backward kernel emits gP in fp32 (atomics) and the
+    two weight/input-gradient GEMMs run on it directly in TF32 — no cast passes over the
+    (B,N,(S+1)C) tensors.  One autograd node, so the fp32 gP never gets down-cast."""
+
+    @staticmethod
+    def forward(ctx, xyz, idx32, dirn, fm, W, bias, S, C):
+        xyz = _need(xyz, torch.float32, "xyz")
+        idx32 = _need(idx32, torch.int32, "idx")
+        dirn = _need(dirn, torch.float32, "dirn")
+        fm = _need(fm, torch.float32, "feature_map")
+        B, N, Cin = fm.shape
+        with torch.autocast("cuda", enabled=False):
+            P = torch.addmm(bias.to(torch.bfloat16), fm.reshape(B * N, Cin).to(torch.bfloat16),
+                            W.to(torch.bfloat16)).view(B, N, (S + 1) * C)
+        need_grad = any(ctx.needs_input_grad)
+        out, am = _graph_conv_fwd_raw(xyz, idx32, dirn, P, S, C, need_grad)
+        if need_grad:
+            ctx.save_for_backward(xyz, idx32, dirn, P, am, fm, W)
+        ctx.dims = (S, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        xyz, idx32, dirn, P, am, fm, W = ctx.saved_tensors
+        S, C = ctx.dims
+        B, N, Cin = fm.shape
+        gout = _need(gout.float(), torch.float32, "gout")
+        gP, gdirn = _graph_conv_bwd_raw(xyz, idx32, dirn, P, am, gout, S, C)
+        gP2 = gP.view(B * N, (S + 1) * C)
+        with torch.autocast("cuda", enabled=False):
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = True
+            try:
+                gfm = (gP2 @ W.t()).view(B, N, Cin) if ctx.needs_input_grad[3] else None
+                gW = fm.reshape(B * N, Cin).t() @ gP2
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
+            gb = gP2.sum(dim=0)
+        return None, None, gdirn, gfm, gW, gb, None, None
+
+
+def hs_conv_mixed(xyz, idx32, dirn, fm, W, bias, S, C):
+    return _HSConvMixed.apply(xyz, idx32, dirn, fm, W, bias, S, C)
 
 
 # ---------------------------------------------------------------- gathers
@@ -289,7 +352,7 @@ class _GatherRows(torch.autograd.Function):
         M = nn32.shape[1]
         with torch.cuda.device(feat.device):
             out = torch.empty(B, M, C, dtype=torch.float32, device=feat.device)
-            _call("hsp_upsample_rows_fwd", _p(feat), _p(nn32), B, Nsrc, M, C, _p(out), C, 0,
+            _call("hsp_upsample_rows_fwd", _p(feat), _p(nn32), B, Nsrc, M, C, _p(out), C, 0, F32,
                   _stream())
         ctx.save_for_backward(nn32)
         ctx.dims = (B, Nsrc, M, C)
@@ -303,7 +366,7 @@ class _GatherRows(torch.autograd.Function):
         gout = _need(gout.float(), torch.float32, "gout")
         with torch.cuda.device(gout.device):
             gfeat = torch.zeros(B, Nsrc, C, dtype=torch.float32, device=gout.device)
-            _call("hsp_upsample_rows_bwd", _p(gout), _p(nn32), B, Nsrc, M, C, C, 0, _p(gfeat),
+            _call("hsp_upsample_rows_bwd", _p(gout), _p(nn32), B, Nsrc, M, C, C, 0, F32, _p(gfeat),
                   _stream())
         return gfeat, None
 
@@ -314,22 +377,26 @@ def gather_rows(feat, nn32):
 
 
 class _ConcatUpsample(torch.autograd.Function):
-    """feat (B,M,sum C_i) = cat_i rows(piece_i): piece_i is copied as is (nn None,
-    Nsrc == M), gathered through a nearest-neighbour table nn_i (B,M) int32, or
-    broadcast over points ((B,C) piece).  One launch per piece, straight into
-    the concat buffer (FaceRecon.py:100-107 without the intermediate tensors)."""
+    """feat (B,M,ld) = cat_i rows(piece_i) [+ zero padding up to ld]: piece_i is copied as
+    is (nn None, Nsrc == M), gathered through a nearest-neighbour table nn_i (B,M) int32,
+    or broadcast over points ((B,C) piece).  One launch per piece, straight into the
+    concat buffer (FaceRecon.py:100-107 without the intermediate tensors); the buffer
+    may be bf16 and padded to an aligned row length for the tensor-core MLPs."""
 
     @staticmethod
-    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, M, nns, *pieces):
+    def forward(ctx, M, nns, ld, out_dtype, *pieces):
         pieces = [_need(p, torch.float32, "piece") for p in pieces]
         B = pieces[0].shape[0]
         widths = [p.shape[-1] for p in pieces]
-        ldo = sum(widths)
+        tot = sum(widths)
+        ld = tot if ld is None else ld
         dev = pieces[0].device
+        dt = BF16 if out_dtype == torch.bfloat16 else F32
         nn32 = []
         with torch.cuda.device(dev):
-            out = torch.empty(B, M, ldo, dtype=torch.float32, device=dev)
+            out = torch.empty(B, M, ld, dtype=out_dtype, device=dev)
+            if ld > tot:
+                out[:, :, tot:].zero_()
             col = 0
             for p, nn, w in zip(pieces, nns, widths):
                 if isinstance(nn, str):  # "bcast": (B,C) -> every point
@@ -341,45 +408,95 @@ class _ConcatUpsample(torch.autograd.Function):
                 else:
                     nsrc, t = p.shape[1], _need(nn, torch.int32, "nn")
                 nn32.append(t)
-                _call("hsp_upsample_rows_fwd", _p(p), _p(t), B, nsrc, M, w, _p(out), ldo, col,
+                _call("hsp_upsample_rows_fwd", _p(p), _p(t), B, nsrc, M, w, _p(out), ld, col, dt,
                       _stream())
                 col += w
         ctx.save_for_backward(*[t for t in nn32 if t is not None])
-        ctx.meta = (B, M, ldo, widths, [None if t is None else True for t in nn32],
+        ctx.meta = (B, M, ld, dt, widths, [t is not None for t in nn32],
                     [isinstance(nn, str) for nn in nns], [p.shape[1] if p.dim() == 3 else 1 for p in pieces])
         return out
 
     @staticmethod
-    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gout):
-        B, M, ldo, widths, has_nn, bcast, nsrcs = ctx.meta
+        B, M, ld, dt, widths, has_nn, bcast, nsrcs = ctx.meta
         saved = list(ctx.saved_tensors)
-        gout = _need(gout.float(), torch.float32, "gout")
+        gout = _need(gout, torch.bfloat16 if dt == BF16 else torch.float32, "gout")
         grads, col = [], 0
         with torch.cuda.device(gout.device):
             for i, w in enumerate(widths):
-                if not ctx.needs_input_grad[2 + i]:
+                nn = saved.pop(0) if has_nn[i] else None
+                if not ctx.needs_input_grad[4 + i]:
                     grads.append(None)
-                    if has_nn[i]:
-                        saved.pop(0)
                 elif bcast[i]:
-                    grads.append(gout[:, :, col:col + w].sum(dim=1))
-                elif has_nn[i]:
-                    nn = saved.pop(0)
-                    g = torch.zeros(B, nsrcs[i], w, dtype=torch.float32, device=gout.device)
-                    _call("hsp_upsample_rows_bwd", _p(gout), _p(nn), B, nsrcs[i], M, w, ldo, col,
+                    grads.append(gout[:, :, col:col + w].float().sum(dim=1))
+                else:
+                    if nn is not None:
+                        g = torch.zeros(B, nsrcs[i], w, dtype=torch.float32, device=gout.device)
+                    else:
+                        g = torch.empty(B, M, w, dtype=torch.float32, device=gout.device)
+                    _call("hsp_upsample_rows_bwd", _p(gout), _p(nn), B, nsrcs[i], M, w, ld, col, dt,
                           _p(g), _stream())
                     grads.append(g)
-                else:
-                    grads.append(gout[:, :, col:col + w])
                 col += w
-        return (None, None, *grads)
+        return (None, None, None, None, *grads)
 
 
-def concat_upsample(pieces, nns, M):
+def concat_upsample(pieces, nns, M, ld=None, out_dtype=torch.float32):
     """K5c + concat.  pieces[i]: (B,M,C) with nns[i] None, (B,Nsrc,C) with nns[i] a
-    (B,M) int32 nearest table, or (B,C) with nns[i] == "bcast"."""
-    return _ConcatUpsample.apply(M, list(nns), *pieces)
+    (B,M) int32 nearest table, or (B,C) with nns[i] == "bcast".  Columns past the
+    pieces (up to ld) are zero."""
+    return _ConcatUpsample.apply(M, list(nns), ld, out_dtype, *pieces)
+
+
+# ------------------------------------------------------------ BatchNorm + ReLU
+class _BnRelu(torch.autograd.Function):
+    """Batch-statistics BatchNorm1d (+ReLU) on a (M,C) matrix (K6b); x may be a column
+    slice (stride (ld,1)) of a wider matrix.  Updates the running statistics in place."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, relu):
+        if not x.is_cuda or x.dim() != 2 or x.stride(1) != 1:
+            raise _lib.HSPoseLibraryError("bn_relu: expected a CUDA (M,C) matrix with unit column stride")
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"bn_relu: unsupported dtype {x.dtype}")
+        M, C = x.shape
+        dt = BF16 if x.dtype == torch.bfloat16 else F32
+        gamma = gamma.float().contiguous()
+        beta = beta.float().contiguous()
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            y = torch.empty(M, C, dtype=x.dtype, device=x.device)
+            stats = torch.empty(4, C, dtype=torch.float32, device=x.device)  # mean, invstd, scale, shift
+            ws = _workspace(lib.hsp_bn_workspace_bytes(M, C), x.device)
+            _call("hsp_bn_relu_fwd", _p(x), x.stride(0), M, C, dt, _p(gamma), _p(beta), float(eps),
+                  float(momentum), int(relu), _p(running_mean), _p(running_var), _p(stats[0]),
+                  _p(stats[1]), _p(stats[2]), _p(y), C, _p(ws), ws.numel(), _stream())
+        ctx.save_for_backward(x, gamma, beta, stats)
+        ctx.relu = int(relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, stats = ctx.saved_tensors
+        M, C = x.shape
+        dt = BF16 if x.dtype == torch.bfloat16 else F32
+        dy = dy.to(x.dtype)
+        if dy.stride(1) != 1 or (dy.stride(0) * dy.element_size()) % 16 != 0:
+            dy = dy.contiguous()
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            dx = torch.empty(M, C, dtype=x.dtype, device=x.device)
+            dgb = torch.empty(2, C, dtype=torch.float32, device=x.device)
+            ws = _workspace(lib.hsp_bn_workspace_bytes(M, C), x.device)
+            _call("hsp_bn_relu_bwd", _p(x), x.stride(0), _p(dy), dy.stride(0), M, C, dt, _p(gamma),
+                  _p(beta), _p(stats[0]), _p(stats[1]), ctx.relu, _p(dgb[0]), _p(dgb[1]), _p(dx), C,
+                  _p(ws), ws.numel(), _stream())
+        return dx, dgb[0], dgb[1], None, None, None, None, None
+
+
+def bn_relu(x, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, relu=True):
+    """y = relu?(batchnorm_train(x)) over the rows of the (M,C) matrix x."""
+    return _BnRelu.apply(x, gamma, beta, running_mean, running_var, eps, momentum, relu)
 
 
 # ---------------------------------------------------------------- chamfer

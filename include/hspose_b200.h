@@ -35,6 +35,10 @@ extern "C" {
 #define HSP_EDEVICE    -3   /* device is not sm_100 (Blackwell B200)               */
 #define HSP_EWORKSPACE -4   /* workspace too small / missing                       */
 
+/* Storage types of the dense (M,C) activation matrices (arithmetic is fp32). */
+#define HSP_DTYPE_F32   0
+#define HSP_DTYPE_BF16  1
+
 /* Distance formulas (evaluation order matters: KNN indices are bit-exact). */
 #define HSP_DIST_NEIGHBOR 0 /* ((-2*inner) + q[j]) + q[i]     gcn3d.py:19-21 */
 #define HSP_DIST_NEAREST  1 /* (s[j] + t[i]) - (2*inner)      gcn3d.py:31-34 */
@@ -98,15 +102,16 @@ int hsp_surface_conv_bwd(const float* xyz, const int32_t* idx, const float* dirn
  * P (B,N,(S+1)*C) = feature_map @ weights + bias (dense GEMM done by the
  * caller); idx = feature-space neighbours; rhat from xyz of those neighbours.
  * argmax (B,N,S*C) uint8 (optional, may be NULL) receives the winning n for
- * the backward pass.                                                        */
+ * the backward pass.  P is fp32 or bf16 (p_dtype = HSP_DTYPE_*; bf16 halves the
+ * gather traffic in the mixed-precision train step); gP is always fp32.      */
 int hsp_graph_conv_fwd(const float* xyz, const int32_t* idx, const float* dirn,
-                       const float* P, int B, int N, int k, int S, int C,
+                       const void* P, int p_dtype, int B, int N, int k, int S, int C,
                        float* out, uint8_t* argmax, void* stream);
 /* Backward: gP (B,N,(S+1)*C) (overwritten: centre part = gout, support part
  * = scatter of gout/S*theta to the winning neighbour rows), gdirn (3,S*C).  */
 size_t hsp_graph_conv_bwd_workspace_bytes(int B, int N, int k, int S, int C);
 int hsp_graph_conv_bwd(const float* xyz, const int32_t* idx, const float* dirn,
-                       const float* P, const uint8_t* argmax, const float* gout,
+                       const void* P, int p_dtype, const uint8_t* argmax, const float* gout,
                        int B, int N, int k, int S, int C, float* gP, float* gdirn,
                        void* workspace, size_t workspace_bytes, void* stream);
 
@@ -144,10 +149,15 @@ int hsp_orl_global_bwd(const float* gG, const int32_t* idx, const uint8_t* argma
  * identity (Nsrc == M: row i) or broadcast (Nsrc == 1: row 0) copy, so the
  * whole torch.cat of FaceRecon.py:107 is served by this one entry point.    */
 int hsp_upsample_rows_fwd(const float* feat, const int32_t* nn, int B, int Nsrc,
-                          int M, int C, float* out, int ldo, int col0, void* stream);
-/* gfeat (B,Nsrc,C) += sum over i with nn[b,i]==r of gout[b,i,col0:col0+C].   */
-int hsp_upsample_rows_bwd(const float* gout, const int32_t* nn, int B, int Nsrc,
-                          int M, int C, int ldo, int col0, float* gfeat, void* stream);
+                          int M, int C, void* out, int ldo, int col0, int out_dtype,
+                          void* stream);
+/* gfeat (B,Nsrc,C) += sum over i with nn[b,i]==r of gout[b,i,col0:col0+C]  (nn != NULL;
+ * gfeat zero-initialised by the caller), or gfeat = gout[..., col0:col0+C] (nn == NULL,
+ * Nsrc == M).  out / gout are fp32 or bf16 (HSP_DTYPE_*): the (B,M,ldo) concat
+ * buffer feeds the bf16 tensor-core MLPs directly.                          */
+int hsp_upsample_rows_bwd(const void* gout, const int32_t* nn, int B, int Nsrc,
+                          int M, int C, int ldo, int col0, int gout_dtype, float* gfeat,
+                          void* stream);
 
 /* ------------------------------------------------------------------ K7 ---
  * Chamfer distance (tools/pyTorchChamferDistance/chamfer_distance.cu:6-187):
@@ -162,6 +172,28 @@ int hsp_chamfer_fwd(const float* a, const float* b, int B, int N, int M,
 int hsp_chamfer_bwd(const float* a, const float* b, const int32_t* idx_a,
                     const int32_t* idx_b, const float* gdist_a, const float* gdist_b,
                     int B, int N, int M, float* ga, float* gb, void* stream);
+
+/* ----------------------------------------------------------------- K6b ---
+ * Batch-statistics BatchNorm1d (+ optional ReLU) over the channel axis of a
+ * row-major (M,C) activation matrix: the BatchNorm1d -> ReLU pairs of the dense
+ * per-point MLPs (FaceRecon.py:38-68,89-95; PoseR.py:22-29; PoseTs.py:24-34) in
+ * training mode.  x / y / dy / dx may be column slices of wider matrices (row
+ * strides ld*, in elements; 16-byte aligned; C % 8 == 0).  dtype = HSP_DTYPE_*.
+ *   fwd: mean, invstd (C each) and scale_shift (2C) are outputs kept for the
+ *        backward; running_mean / running_var (may be NULL) are updated with
+ *        `momentum` (unbiased variance), as nn.BatchNorm1d does.
+ *   bwd: dgamma, dbeta (C each), dx.  The ReLU mask is recomputed from x.
+ * Deterministic (fixed-order partial sums through `workspace`).             */
+size_t hsp_bn_workspace_bytes(int M, int C);
+int hsp_bn_relu_fwd(const void* x, int ldx, int M, int C, int dtype, const float* gamma,
+                    const float* beta, float eps, float momentum, int relu,
+                    float* running_mean, float* running_var, float* mean, float* invstd,
+                    float* scale_shift, void* y, int ldy, void* workspace,
+                    size_t workspace_bytes, void* stream);
+int hsp_bn_relu_bwd(const void* x, int ldx, const void* dy, int lddy, int M, int C, int dtype,
+                    const float* gamma, const float* beta, const float* mean,
+                    const float* invstd, int relu, float* dgamma, float* dbeta, void* dx,
+                    int lddx, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -94,3 +94,31 @@ def test_native_losses_match_reference(golden):
     assert sorted(keys) == sorted(out.keys())
     for k in keys:
         np.testing.assert_allclose(out[k].item(), g["loss_fs_" + k].item(), rtol=1e-5, atol=1e-6, err_msg=k)
+
+
+def replay_train_samples(bs=4, n=1028, seed=4321):
+    """The golden train step ran on CPU, where HSPose.data_augment's torch.rand calls
+    (reference HSPose.py:233-246, data_augmentation.py:109-110,136) advance the SAME generator
+    Pool_layer's randperm uses.  Replay those draws to recover the two pooling samples."""
+    torch.manual_seed(seed)
+    for shape in [(bs, 1)] * 6 + [(bs, n, 3)]:
+        torch.rand(shape)
+    s1 = torch.randperm(n)[: n // 4]
+    s2 = torch.randperm(n // 4)[: (n // 4) // 4]
+    return s1, s2
+
+
+def test_oracle_train_forward_teacher_forced(golden):
+    """Train-mode (batch-stat BN, dropout off) oracle forward vs the reference's HSPose run."""
+    g = golden("e2e_train")
+    sd = _module(1).state_dict()
+    batch = synth_batch(4, 1028, seed=2, train=True)
+    rf = [torch.from_numpy(g[f"rf{i}"].astype(np.int64)) for i in range(4)]
+    with torch.no_grad():
+        out = to.posenet9d({k: v.clone() for k, v in sd.items()}, batch["PC"], batch["obj_id"], k=20,
+                           train=True, bn_training=True, samples=replay_train_samples(), rf_indices=rf)
+    for n in NAMES:
+        np.testing.assert_allclose(out[n].numpy(), g["out_" + n], atol=1e-4, err_msg=n)  # bn3 normalises over 4 samples
+    for n in ("recon", "face_dis", "face_f", "face_normal"):
+        np.testing.assert_allclose(out[n][:, ::64].numpy(), g["out_" + n],
+                                   atol=1e-3 if n == "face_normal" else 1e-4, err_msg=n)  # fn/|fn|, |fn| small

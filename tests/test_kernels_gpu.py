@@ -272,3 +272,97 @@ def test_chamfer_vs_oracle(cuda):
     (gda.mean() + gdb.mean()).backward()
     np.testing.assert_allclose(ac.grad.cpu().numpy(), a.grad.numpy(), atol=1e-6)
     np.testing.assert_allclose(bc.grad.cpu().numpy(), b.grad.numpy(), atol=1e-6)
+
+
+# ----------------------------------------------------------------- K6b (BatchNorm + ReLU)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,C,ld,relu", [(4112, 128, 128, True), (1028, 256, 3584, True),
+                                         (777, 512, 512, False), (64, 1024, 1032, True)])
+def test_bn_relu_fwd_bwd_vs_torch(cuda, dtype, M, C, ld, relu):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + C)
+    wide = (torch.randn(M, ld, generator=g) * 1.5 + 0.3).to(cuda).to(dtype)
+    x = wide[:, ld - C:] if ld > C and (ld - C) % 8 == 0 else wide[:, :C]
+    gamma = (torch.rand(C, generator=g) + 0.5).to(cuda).requires_grad_()
+    beta = (torch.randn(C, generator=g) * 0.2).to(cuda).requires_grad_()
+    rm, rv = torch.zeros(C, device=cuda), torch.ones(C, device=cuda)
+    rm2, rv2 = rm.clone(), rv.clone()
+    gy = torch.randn(M, C, generator=g).to(cuda).to(dtype)
+
+    xr = x.detach().float().requires_grad_()
+    g2, b2 = gamma.detach().clone().requires_grad_(), beta.detach().clone().requires_grad_()
+    ref = torch.nn.functional.batch_norm(xr, rm2, rv2, g2, b2, True, 0.1, 1e-5)
+    if relu:
+        ref = torch.relu(ref)
+    ref.backward(gy.float())
+
+    xc = x.detach().requires_grad_()
+    y = ops.bn_relu(xc, gamma, beta, rm, rv, 1e-5, 0.1, relu)
+    y.backward(gy)
+    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    np.testing.assert_allclose(y.detach().float().cpu().numpy(), ref.detach().cpu().numpy(), atol=tol, rtol=tol)
+    np.testing.assert_allclose(rm.cpu().numpy(), rm2.cpu().numpy(), atol=1e-5)
+    np.testing.assert_allclose(rv.cpu().numpy(), rv2.cpu().numpy(), atol=1e-4)
+    gs = max(1.0, g2.grad.abs().max().item())
+    np.testing.assert_allclose(gamma.grad.cpu().numpy(), g2.grad.cpu().numpy(), atol=tol * gs * 3, rtol=tol)
+    np.testing.assert_allclose(beta.grad.cpu().numpy(), b2.grad.cpu().numpy(), atol=tol * gs * 3, rtol=tol)
+    np.testing.assert_allclose(xc.grad.float().cpu().numpy(), xr.grad.cpu().numpy(), atol=tol, rtol=tol)
+
+
+def test_concat_upsample_bf16_padded(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    B, M, Ns = 2, 300, 75
+    a = torch.randn(B, M, 128, generator=g).to(cuda).requires_grad_()
+    b = torch.randn(B, Ns, 256, generator=g).to(cuda).requires_grad_()
+    oh = torch.randn(B, 6, generator=g).to(cuda)
+    xyz = torch.randn(B, M, 3, generator=g).to(cuda)
+    nn = torch.randint(0, Ns, (B, M), generator=g).to(cuda)
+    out = ops.concat_upsample([a, b, oh, xyz], [None, nn.int(), "bcast", None], M, ld=400,
+                              out_dtype=torch.bfloat16)
+    assert out.dtype == torch.bfloat16 and tuple(out.shape) == (B, M, 400)
+    ref = torch.cat([a, torch.gather(b, 1, nn[..., None].expand(-1, -1, 256)),
+                     oh[:, None, :].expand(-1, M, -1), xyz,
+                     torch.zeros(B, M, 400 - 393, device=cuda)], dim=2)
+    assert torch.equal(out, ref.to(torch.bfloat16))
+    go = torch.randn(B, M, 400, generator=g).to(cuda).to(torch.bfloat16)
+    out.backward(go)
+    ref.backward(go.float())
+    ga, gb = a.grad.clone(), b.grad.clone()
+    assert torch.allclose(ga, go[:, :, :128].float())
+    a.grad = b.grad = None
+    ref2 = torch.gather(b, 1, nn[..., None].expand(-1, -1, 256))
+    ref2.backward(go[:, :, 128:384].float())
+    assert torch.allclose(gb, b.grad, atol=1e-5)
+
+
+def test_graph_conv_bf16_P_and_mixed_layer(cuda):
+    """bf16 storage of P: kernel result equals the fp32 kernel on the bf16-rounded P; the fused
+    mixed-precision autograd node agrees with the fp32 path within bf16 tolerance."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(12)
+    B, N, k, S, C, Cin = 2, 257, 20, 7, 128, 128
+    xyz = (torch.randn(B, N, 3, generator=g) * 0.05).to(cuda)
+    fm = torch.relu(torch.randn(B, N, Cin, generator=g)).to(cuda)
+    W = ((torch.rand(Cin, (S + 1) * C, generator=g) * 2 - 1) / (C ** 0.5)).to(cuda)
+    bias = ((torch.rand((S + 1) * C, generator=g) * 2 - 1) * 0.1).to(cuda)
+    dirn = torch.nn.functional.normalize((torch.rand(3, S * C, generator=g) * 2 - 1), dim=0).to(cuda)
+    idx = ops.knn_feat(fm, k)[1]
+    P16 = (fm @ W + bias).to(torch.bfloat16)
+    o16, _ = ops._graph_conv_fwd_raw(xyz, idx, dirn, P16, S, C, False)
+    o32, _ = ops._graph_conv_fwd_raw(xyz, idx, dirn, P16.float(), S, C, False)
+    assert torch.equal(o16, o32)
+    # fused mixed node vs fp32 autograd path
+    Wm, bm, dm = W.clone().requires_grad_(), bias.clone().requires_grad_(), dirn.clone().requires_grad_()
+    fmm = fm.clone().requires_grad_()
+    om = ops.hs_conv_mixed(xyz, idx, dm, fmm, Wm, bm, S, C)
+    Wf, bf, df = W.clone().requires_grad_(), bias.clone().requires_grad_(), dirn.clone().requires_grad_()
+    fmf = fm.clone().requires_grad_()
+    of = ops.graph_conv(xyz, idx, df, fmf @ Wf + bf, S, C)
+    go = torch.randn(B, N, C, generator=g).to(cuda)
+    om.backward(go)
+    of.backward(go)
+    assert torch.allclose(om, of, atol=3e-2, rtol=3e-2)
+    for a, b_ in ((Wm.grad, Wf.grad), (bm.grad, bf.grad), (fmm.grad, fmf.grad), (dm.grad, df.grad)):
+        rel = (a - b_).norm() / b_.norm()
+        assert rel < 3e-2, rel
