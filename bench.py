@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=4, help="objects per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of one CUDA graph")
     return ap.parse_args()
 
 
@@ -55,6 +56,7 @@ def workload_config(args, world):
             "precision": "bf16 autocast dense GEMMs; fp32 KNN/graph-conv kernels"
             if args.precision == "bf16" else "fp32",
             "parallelism": f"dp{world} (batch sharded, one NCCL grad all-reduce)",
+            "launch": "eager" if args.no_graph else "whole step replayed as one CUDA graph",
             "l2": "per-step working set (>2 GB of activations at batch 128) exceeds the 126 MB L2; "
                   "no explicit flush"}
 
@@ -215,6 +217,7 @@ def run_b200(args):
 
     import hspose_b200.ops as ops
     from hspose_b200 import _lib, parallel
+    from hspose_b200.engine import TrainStep
     from hspose_b200.HSPose import HSPose
     from oracle.synth import synth_batch  # seeded synthetic inputs only (no oracle compute)
 
@@ -229,30 +232,20 @@ def run_b200(args):
 
     torch.manual_seed(0)                       # identical weights on every rank
     model = HSPose("PoseNet_only", chamfer_w=1.0).to(dev).train()
-    flat = parallel.FlatGradients(model.posenet.parameters())
-    opt = torch.optim.Adam(flat.params, lr=1e-4, fused=True)
     parallel.seed_all(1234)                    # same Pool_layer permutations on every rank
+    amp = args.precision == "bf16"
+    trainer = TrainStep(model, lr=1e-4, clip=5.0, amp=amp, graph=not args.no_graph)
 
     B = args.batch
     host = {k: v.pin_memory() for k, v in synth_batch(B, N_PTS, seed=1 + rank, train=True).items()}
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
-    amp = args.precision == "bf16"
 
     def step(batch):
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
-            _, losses = model(**batch, do_loss=True)
-        total = sum(v.reshape(()).float() for grp in losses.values() for v in grp.values())
-        flat.zero()
-        total.backward()
-        flat.all_reduce_mean()
-        flat.clip_(5.0)
-        opt.step()
-        return total
+        return trainer(batch)
 
     def step_e2e():
-        batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        return step(batch).item()              # D2H of the loss: 4 bytes, synchronises
+        return trainer(host).item()            # H2D of the 12 inputs + D2H of the loss (4 bytes)
 
     def barrier():
         if world > 1:
@@ -279,6 +272,8 @@ def run_b200(args):
     l0 = ops.launch_count()
     ms_step = timed(lambda: step(resident), args.steps)
     launches = ops.launch_count() - l0
+    if trainer.launches_per_step is not None:   # graph replay: kernels recorded at capture time
+        launches = trainer.launches_per_step * args.steps
     clocks = sampler.stop()
     for _ in range(2):
         step_e2e()
@@ -286,6 +281,7 @@ def run_b200(args):
 
     # per-kernel CUDA-event timing of the same step (separate instrumented pass)
     ksteps = min(3, args.steps)
+    trainer.use_graph = False
     ops.enable_timing(True)
     for _ in range(ksteps):
         step(resident)

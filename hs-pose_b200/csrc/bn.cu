@@ -68,7 +68,7 @@ static BnGeom bn_geom(int M, int C) {
   while (g.ct > 1 && (cv % g.ct) != 0) g.ct >>= 1;
   g.rl = BN_THREADS / g.ct;
   g.ctiles = cv / g.ct;
-  long want = (148L * 8 + g.ctiles - 1) / g.ctiles;
+  long want = (148L * 6 + g.ctiles - 1) / g.ctiles;
   long maxr = (M + g.rl * 4 - 1) / (g.rl * 4);
   if (want > maxr) want = maxr;
   if (want < 1) want = 1;
@@ -134,6 +134,28 @@ bn_reduce_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, int
   }
 }
 
+// Fixed-order sum of the per-CTA partials of 32 channels: block (32, 8), row group ry takes
+// chunks ry, ry+8, ...; the 8 group sums are then added in order 0..7 (deterministic).
+__device__ __forceinline__ void bn_sum_partials(const float* __restrict__ partial, int rchunks,
+                                                int C, int c, double& s, double& q) {
+  __shared__ double sh[2][8][32];
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (int r = threadIdx.y; r < rchunks; r += 8) {
+      a += (double)partial[((size_t)r * 2) * C + c];
+      b += (double)partial[((size_t)r * 2 + 1) * C + c];
+    }
+  }
+  sh[0][threadIdx.y][threadIdx.x] = a;
+  sh[1][threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  s = 0.0; q = 0.0;
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) { s += sh[0][g][threadIdx.x]; q += sh[1][g][threadIdx.x]; }
+  }
+}
+
 // Forward finalize: mean / invstd, fused affine (scale, shift), running-stat update.
 __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int rchunks, int M, int C,
                                        float eps, float momentum, const float* __restrict__ gamma,
@@ -141,13 +163,10 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int rc
                                        float* __restrict__ invstd, float* __restrict__ scale,
                                        float* __restrict__ shift, float* __restrict__ running_mean,
                                        float* __restrict__ running_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int r = 0; r < rchunks; ++r) {
-    s += (double)partial[((size_t)r * 2) * C + c];
-    q += (double)partial[((size_t)r * 2 + 1) * C + c];
-  }
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, q;
+  bn_sum_partials(partial, rchunks, C, c, s, q);
+  if (threadIdx.y != 0 || c >= C) return;
   const double m = s / M;
   double var = q / M - m * m;
   if (var < 0.0) var = 0.0;
@@ -167,13 +186,10 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int rc
 // Backward finalize: dgamma = sum dy' xhat, dbeta = sum dy'.
 __global__ void bn_finalize_bwd_kernel(const float* __restrict__ partial, int rchunks, int C,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int r = 0; r < rchunks; ++r) {
-    s += (double)partial[((size_t)r * 2) * C + c];
-    q += (double)partial[((size_t)r * 2 + 1) * C + c];
-  }
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, q;
+  bn_sum_partials(partial, rchunks, C, c, s, q);
+  if (threadIdx.y != 0 || c >= C) return;
   dbeta[c] = (float)s;
   dgamma[c] = (float)q;
 }
@@ -277,7 +293,7 @@ extern "C" int hsp_bn_relu_fwd(const void* x, int ldx, int M, int C, int dtype, 
     bn_reduce_kernel<float, 0><<<grid, BN_THREADS, 0, st>>>(
         (const float*)x, ldx, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, M, C, g.ct, part);
   HSP_LAUNCH_CHECK();
-  bn_finalize_fwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, g.rchunks, M, C, eps, momentum, gamma,
+  bn_finalize_fwd_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(part, g.rchunks, M, C, eps, momentum, gamma,
                                                           beta, mean, invstd, scale, shift,
                                                           running_mean, running_var);
   HSP_LAUNCH_CHECK();
@@ -313,7 +329,7 @@ extern "C" int hsp_bn_relu_bwd(const void* x, int ldx, const void* dy, int lddy,
                                                             lddy, mean, invstd, gamma, beta, relu, M,
                                                             C, g.ct, part);
   HSP_LAUNCH_CHECK();
-  bn_finalize_bwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, g.rchunks, C, dgamma, dbeta);
+  bn_finalize_bwd_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(part, g.rchunks, C, dgamma, dbeta);
   HSP_LAUNCH_CHECK();
   if (dtype == HSP_DTYPE_BF16)
     bn_bwd_apply_kernel<__nv_bfloat16><<<grid, BN_THREADS, 0, st>>>(

@@ -26,6 +26,7 @@ from . import ops
 # of the ascending list (exact: our order is total on (distance, index)).
 # --------------------------------------------------------------------------
 _cache = None
+_pool_rows_provider = None   # callable(vertice_num, pool_num, device) -> (pool_num,) int32 device rows
 _forced_rf = None     # list of (B,N,k) index tensors consumed in order (teacher forcing, protocol T2)
 _recorded_rf = None   # list receiving the RF-F tables a forward produced
 
@@ -38,6 +39,15 @@ def neighbor_cache():
         yield
     finally:
         _cache = prev
+
+
+def set_pool_rows_provider(fn):
+    """Route Pool_layer's sample draw through `fn` (engine.TrainStep uses it to feed the
+    permutation from a static device buffer so the whole step can live in a CUDA graph; the
+    draw itself is still `torch.randperm(vertice_num)[:pool_num]` on the CPU generator)."""
+    global _pool_rows_provider
+    prev, _pool_rows_provider = _pool_rows_provider, fn
+    return prev
 
 
 @contextlib.contextmanager
@@ -244,8 +254,11 @@ class Pool_layer(nn.Module):
         bs, vertice_num, _ = vertices.size()
         table, kk = _geo_index32(vertices, self.neighbor_num)
         pool_num = int(vertice_num / self.pooling_rate)
-        sample_idx = torch.randperm(vertice_num)[:pool_num]
-        rows = sample_idx.to(device=vertices.device, dtype=torch.int32, non_blocking=True)
+        if _pool_rows_provider is not None:
+            rows = _pool_rows_provider(vertice_num, pool_num, vertices.device)
+        else:
+            sample_idx = torch.randperm(vertice_num)[:pool_num]
+            rows = sample_idx.to(device=vertices.device, dtype=torch.int32, non_blocking=True)
         vertices_pool = ops.gather_rows(vertices, rows.unsqueeze(0).expand(bs, -1).contiguous())
         # max over the 4 nearest evaluated ONLY at the sampled rows (K5b)
         feature_map_pool = ops.gather_max(feature_map, table, rows, kuse=self.neighbor_num)
