@@ -19,7 +19,7 @@ def _to_camera_frame(pc_obj, R, t):
 
 
 def deform_bb(pc, model_point, R, t, s, sym, aug_bb):
-    sym_aug = (aug_bb + aug_bb[:, [2, 1, 0]]) / 2.0
+    sym_aug = (aug_bb + aug_bb.flip(-1)) / 2.0   # == aug_bb[:, [2, 1, 0]] without a host index tensor
     scale = torch.where((sym[:, 0] == 1).unsqueeze(-1), sym_aug, aug_bb)
     pc_new = _to_camera_frame(_to_object_frame(pc, R, t) * scale.unsqueeze(1), R, t)
     return pc_new, s * scale, model_point * scale.unsqueeze(1)

@@ -154,6 +154,150 @@ graph_conv_fwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__
 
 
 
+// ---------------------------------------------------------------------------
+// K4 forward, v2: two adjacent channels per thread on the packed-FP32 datapath.
+//
+// The v1 kernel above is issue-bound (ncu: 78 % issue-active, 6 % DRAM): ~16
+// instructions per (neighbour, support, channel) element, half of them on the
+// ALU pipe.  Here a thread owns the channel PAIR (c, c+1) of one point:
+//   * theta for both channels is 3 packed instructions (FMUL2 + 2 FFMA2, sm_100
+//     `__ffma2_rn`) on pre-halved unit directions d/2, and ReLU is the exact
+//     identity  relu(t) = t/2 + |t/2|  (one FADD with a free |.| modifier) —
+//     FMA pipe instead of an ALU-pipe FMNMX; bit-identical to max(t, 0);
+//   * the activation product is one FMUL2;
+//   * the support rows are read as one 4-byte (bf16x2) or 8-byte (fp32x2) load
+//     per (neighbour, support): a warp still reads whole 128/256-byte segments;
+//   * unit direction + neighbour index of a (point, neighbour) pair arrive as ONE
+//     16-byte shared-memory broadcast.
+// CTA = 128 threads = (C/2 channel pairs) x (points in parallel), tile of 8 points.
+// ---------------------------------------------------------------------------
+constexpr int GC2_THREADS = 128;
+
+template <typename TP> struct Pair;
+template <> struct Pair<float> {
+  static __device__ __forceinline__ float2 load(const float* p) {
+    return __ldg(reinterpret_cast<const float2*>(p));
+  }
+};
+template <> struct Pair<__nv_bfloat16> {
+  static __device__ __forceinline__ float2 load(const __nv_bfloat16* p) {
+    const unsigned u = __ldg(reinterpret_cast<const unsigned*>(p));
+    // low half via an integer multiply (FMA pipe), high half via one LOP3 (ALU pipe)
+    return make_float2(__uint_as_float(u * 65536u), __uint_as_float(u & 0xffff0000u));
+  }
+};
+
+// AM: 0 = max only (no gradient needed), 1 = exact argmax (3 ALU ops / element: FSETP, FSEL,
+// SEL), 2 = tagged argmax (2 ALU ops: the neighbour slot n replaces the 6 low mantissa bits of
+// the candidate, one LOP3 + one FMNMX; value error <= 2^-17 relative — used with bf16 P, whose
+// own rounding is 2^-9).  CT: compile-time channel count (0 = runtime C) so that the S support
+// loads of a neighbour row are immediate offsets from one base address.
+template <int S, typename TP, int AM, int CT>
+__global__ void __launch_bounds__(GC2_THREADS)
+graph_conv_fwd2_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
+                       const float* __restrict__ dirn, const TP* __restrict__ P, int N, int k,
+                       int Crt, int lanes_c, float* __restrict__ out, uint8_t* __restrict__ argmax) {
+  __shared__ float4 s_rn[GC_PT * GC_MAXK];   // (rhat.x, rhat.y, rhat.z, bits(neighbour index))
+  const int C = CT ? CT : Crt;
+  const int b = blockIdx.y, i0 = blockIdx.x * GC_PT;
+  const int npts = min(GC_PT, N - i0);
+  const int SC = S * C, LD = (S + 1) * C;
+  const float* xb = xyz + (size_t)b * N * 3;
+  const int32_t* ib = idx + (size_t)b * N * k;
+  for (int p = threadIdx.x; p < npts * k; p += GC2_THREADS) {
+    const int i = i0 + p / k;
+    const int nb = ib[(size_t)i * k + (p % k)];
+    float r[3];
+    unit_dir(xb, i, nb, r);
+    s_rn[p] = make_float4(r[0], r[1], r[2], __int_as_float(nb));
+  }
+  const int pts_par = GC2_THREADS / lanes_c;
+  const int lane_c = threadIdx.x % lanes_c, psub = threadIdx.x / lanes_c;
+  const int c = (blockIdx.z * lanes_c + lane_c) * 2;
+  const bool active = psub < pts_par && c < C;
+  float2 dx[S], dy[S], dz[S];
+  if (active) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {   // halved: theta/2 = rhat . (d/2), exact
+      const float2 x2 = *reinterpret_cast<const float2*>(dirn + s * C + c);
+      const float2 y2 = *reinterpret_cast<const float2*>(dirn + SC + s * C + c);
+      const float2 z2 = *reinterpret_cast<const float2*>(dirn + 2 * SC + s * C + c);
+      dx[s] = make_float2(0.5f * x2.x, 0.5f * x2.y);
+      dy[s] = make_float2(0.5f * y2.x, 0.5f * y2.y);
+      dz[s] = make_float2(0.5f * z2.x, 0.5f * z2.y);
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  const TP* Pb = P + (size_t)b * N * LD + C + c;   // support block, this thread's channel pair
+  for (int p = psub; p < npts; p += pts_par) {
+    float2 acc[S];
+    int am0[S], am1[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { acc[s] = make_float2(-INFINITY, -INFINITY); am0[s] = 0; am1[s] = 0; }
+#pragma unroll 2
+    for (int n = 0; n < k; ++n) {
+      const float4 rn = s_rn[p * k + n];
+      const TP* sup = Pb + (size_t)__float_as_int(rn.w) * LD;
+      float2 v[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) v[s] = Pair<TP>::load(sup + s * C);
+      const float2 rx = make_float2(rn.x, rn.x), ry = make_float2(rn.y, rn.y),
+                   rz = make_float2(rn.z, rn.z);
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float2 t = __ffma2_rn(rz, dz[s], __ffma2_rn(ry, dy[s], __fmul2_rn(rx, dx[s])));
+        t.x = __fadd_rn(t.x, fabsf(t.x));      // relu(theta), exact
+        t.y = __fadd_rn(t.y, fabsf(t.y));
+        const float2 a = __fmul2_rn(t, v[s]);
+        if (AM == 1) {
+          if (a.x > acc[s].x) { acc[s].x = a.x; am0[s] = n; }
+          if (a.y > acc[s].y) { acc[s].y = a.y; am1[s] = n; }
+        } else if (AM == 2) {
+          acc[s].x = fmaxf(acc[s].x, __uint_as_float((__float_as_uint(a.x) & 0xffffffc0u) | (unsigned)n));
+          acc[s].y = fmaxf(acc[s].y, __uint_as_float((__float_as_uint(a.y) & 0xffffffc0u) | (unsigned)n));
+        } else {
+          acc[s].x = fmaxf(acc[s].x, a.x);
+          acc[s].y = fmaxf(acc[s].y, a.y);
+        }
+      }
+    }
+    float sx = 0.0f, sy = 0.0f;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      if (AM == 2) {
+        am0[s] = (int)(__float_as_uint(acc[s].x) & 63u);
+        am1[s] = (int)(__float_as_uint(acc[s].y) & 63u);
+        acc[s].x = __uint_as_float(__float_as_uint(acc[s].x) & 0xffffffc0u);
+        acc[s].y = __uint_as_float(__float_as_uint(acc[s].y) & 0xffffffc0u);
+      }
+      sx += acc[s].x; sy += acc[s].y;
+    }
+    const size_t row = (size_t)b * N + i0 + p;
+    const float2 ctr = Pair<TP>::load(Pb + (size_t)(i0 + p) * LD - C);
+    *reinterpret_cast<float2*>(out + row * C + c) =
+        make_float2(ctr.x + __fdiv_rn(sx, (float)S), ctr.y + __fdiv_rn(sy, (float)S));
+    if (AM != 0) {
+#pragma unroll
+      for (int s = 0; s < S; ++s)
+        *reinterpret_cast<uchar2*>(argmax + row * SC + s * C + c) =
+            make_uchar2((unsigned char)am0[s], (unsigned char)am1[s]);
+    }
+  }
+}
+
+template <int S, typename TP, int AM>
+static void launch_gc2(dim3 grid2, cudaStream_t st, const float* xyz, const int32_t* idx,
+                       const float* dirn, const TP* P, int N, int k, int C, int lanes_c, float* out,
+                       uint8_t* argmax) {
+  switch (C) {
+    case 128: graph_conv_fwd2_kernel<S, TP, AM, 128><<<grid2, GC2_THREADS, 0, st>>>(xyz, idx, dirn, P, N, k, C, lanes_c, out, argmax); break;
+    case 256: graph_conv_fwd2_kernel<S, TP, AM, 256><<<grid2, GC2_THREADS, 0, st>>>(xyz, idx, dirn, P, N, k, C, lanes_c, out, argmax); break;
+    case 512: graph_conv_fwd2_kernel<S, TP, AM, 512><<<grid2, GC2_THREADS, 0, st>>>(xyz, idx, dirn, P, N, k, C, lanes_c, out, argmax); break;
+    default:  graph_conv_fwd2_kernel<S, TP, AM, 0><<<grid2, GC2_THREADS, 0, st>>>(xyz, idx, dirn, P, N, k, C, lanes_c, out, argmax); break;
+  }
+}
+
 // get_neighbor_direction_norm (gcn3d.py:49-59) as a stand-alone op (API parity;
 // the fused kernels above never materialise it).
 __global__ void direction_norm_kernel(const float* __restrict__ xyz,
@@ -369,7 +513,19 @@ extern "C" int hsp_graph_conv_fwd(const float* xyz, const int32_t* idx, const fl
   if (B == 0) return HSP_OK;
   dim3 grid((N + GC_PT - 1) / GC_PT, B, (C + GC_THREADS - 1) / GC_THREADS);
   cudaStream_t st = (cudaStream_t)stream;
-  if (p_dtype == HSP_DTYPE_BF16) {
+  if ((C & 1) == 0 && S == 7) {   // v2 (reference default S = 7): channel pairs, packed FP32
+    const int pairs = C / 2;
+    const int lanes_c = pairs < GC2_THREADS ? pairs : GC2_THREADS;
+    dim3 grid2((N + GC_PT - 1) / GC_PT, B, (pairs + lanes_c - 1) / lanes_c);
+#define HSP_GC2(TP_, AM_) \
+    launch_gc2<7, TP_, AM_>(grid2, st, xyz, idx, dirn, (const TP_*)P, N, k, C, lanes_c, out, argmax)
+    if (p_dtype == HSP_DTYPE_BF16) {
+      if (argmax) { HSP_GC2(__nv_bfloat16, 2); } else { HSP_GC2(__nv_bfloat16, 0); }
+    } else {
+      if (argmax) { HSP_GC2(float, 1); } else { HSP_GC2(float, 0); }
+    }
+#undef HSP_GC2
+  } else if (p_dtype == HSP_DTYPE_BF16) {
     HSP_DISPATCH_S(S, (graph_conv_fwd_kernel<S, __nv_bfloat16><<<grid, GC_THREADS, 0, st>>>(
                           xyz, idx, dirn, (const __nv_bfloat16*)P, N, k, C, out, argmax)));
   } else {

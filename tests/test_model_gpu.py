@@ -191,9 +191,12 @@ def test_api_functions_match_oracle(cuda):
 
 
 def test_mixed_precision_step_close_to_fp32(cuda):
-    """bf16 fast path (autocast) vs the fp32 path of the same module on the same batch:
-    losses within bf16 tolerance, gradients with high cosine similarity."""
+    """bf16 fast path (autocast) vs the fp32 path of the same module on the same batch, with
+    the fp32 run's RF-F neighbour tables forced into the bf16 run (removes the KNN
+    discontinuity): losses within bf16 tolerance, gradients with high cosine similarity."""
+    from hspose_b200 import gcn3d
     from hspose_b200.HSPose import HSPose
+    rf = []
     F = _flags()
     saved = {n: getattr(F, n) for n in ("aug_pc_pro", "aug_rt_pro", "aug_bb_pro", "aug_bc_pro")}
     for n in saved:
@@ -208,7 +211,8 @@ def test_mixed_precision_step_close_to_fp32(cuda):
                     m.p = 0.0
             batch = {k: v.to(cuda) for k, v in synth_batch(8, 1028, seed=3, train=True).items()}
             torch.manual_seed(99)
-            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+            ctx = gcn3d.record_rf_indices(rf) if mode == "fp32" else gcn3d.force_rf_indices(rf)
+            with ctx, torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
                 out, losses = net(**batch, do_loss=True)
             total = sum(v.reshape(()).float() for grp in losses.values() for v in grp.values())
             total.backward()
@@ -216,10 +220,9 @@ def test_mixed_precision_step_close_to_fp32(cuda):
             res[mode] = (total.item(), flat, {k: v.item() for k, v in losses["fsnet_loss"].items()})
         t32, g32, l32 = res["fp32"]
         t16, g16, l16 = res["bf16"]
-        # random weights + batch-stat BN over 8 objects + RF-F neighbour flips: loose bound
-        assert abs(t32 - t16) / abs(t32) < 0.1, (t32, t16, l32, l16)
+        assert abs(t32 - t16) / abs(t32) < 5e-2, (t32, t16, l32, l16)
         cos = torch.nn.functional.cosine_similarity(g32, g16, dim=0).item()
-        assert cos > 0.8, cos
+        assert cos > 0.9, cos
     finally:
         for n, v in saved.items():
             setattr(F, n, v)

@@ -49,8 +49,16 @@ def main():
             ms = timeit(lambda: ops.surface_conv(xyz, idx, dirn, S, C))
             res.append(dict(kernel="surface_conv_fwd", B=B, N=N, C=C, ms=ms))
             ms = timeit(lambda: ops.graph_conv(xyz, rf, dirn, P, S, C))
-            res.append(dict(kernel="graph_conv_fwd", B=B, N=N, C=C, ms=ms,
+            res.append(dict(kernel="graph_conv_fwd_f32_nograd", B=B, N=N, C=C, ms=ms,
                             gather_GBs=B * N * k * S * C * 4 / ms / 1e6))
+            ms = timeit(lambda: ops._graph_conv_fwd_raw(xyz, rf, dirn, P, S, C, True))
+            res.append(dict(kernel="graph_conv_fwd_f32_argmax", B=B, N=N, C=C, ms=ms))
+            P16 = P.to(torch.bfloat16)
+            ms = timeit(lambda: ops._graph_conv_fwd_raw(xyz, rf, dirn, P16, S, C, True))
+            res.append(dict(kernel="graph_conv_fwd_bf16_tagged", B=B, N=N, C=C, ms=ms,
+                            gather_GBs=B * N * k * S * C * 2 / ms / 1e6))
+            ms = timeit(lambda: ops._graph_conv_fwd_raw(xyz, rf, dirn, P16, S, C, False))
+            res.append(dict(kernel="graph_conv_fwd_bf16_nograd", B=B, N=N, C=C, ms=ms))
             feat = torch.randn(B, N, C, generator=g).to(dev)
             ms = timeit(lambda: ops.orl_global(feat, idx))
             res.append(dict(kernel="orl_global", B=B, N=N, C=C, ms=ms))
