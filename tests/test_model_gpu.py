@@ -148,17 +148,95 @@ def test_hspose_train_step_teacher_forced(cuda, golden):
             worst = max(worst, abs(mine - v) / max(v, 1e-6))
             # biases in front of a batch-stat BN have zero analytic gradient (rounding noise ~3e-5)
             assert abs(mine - v) <= 2e-3 * v + 1e-4, (n, mine, v)
+        # Element-wise gradients.  Only the three pose heads feed this loss, and each routes its
+        # gradient through max-over-points: 3 x 4 x 256 winning rows carry the whole backbone
+        # gradient, so one ReLU-mask / argmax near-tie decided differently by fp32 rounding moves
+        # every backbone gradient by ~0.1-1 % (measured on B200, tools/debug_grad.py: the
+        # reference's own fp32 gradients are 2e-3..9e-3 away, in relative L2, from the same graph
+        # evaluated in fp64; ours are 3e-4..3e-3 away).  The bar is therefore a relative-L2 bound
+        # at that noise floor; test_train_gradients_vs_fp64_oracle holds the tight bound.
         for key in g:
             if key.startswith("grad::"):
-                p = params[key[len("grad::"):]]
-                ref = g[key]
-                tol = 2e-4 * max(1.0, float(np.abs(ref).max()))
-                bad = np.abs(p.grad.cpu().numpy() - ref) > tol
-                assert bad.mean() < 5e-3, (key, bad.mean())  # isolated argmax near-tie flips only
+                mine = params[key[len("grad::"):]].grad.double().cpu().numpy()
+                ref = g[key].astype(np.float64)
+                if np.linalg.norm(ref) < 1e-3:     # zero analytic gradient (bias in front of a BN)
+                    assert np.abs(mine - ref).max() < 1e-3, key
+                    continue
+                rel = np.linalg.norm(mine - ref) / np.linalg.norm(ref)
+                assert rel < 2e-2, (key, rel)
         sd = net.state_dict()
         for key in g:
             if key.startswith("post::"):
                 np.testing.assert_allclose(sd[key[len("post::"):]].cpu().numpy(), g[key], atol=1e-5)
+    finally:
+        for n, v in saved.items():
+            setattr(F, n, v)
+
+
+def test_train_gradients_vs_fp64_oracle(cuda, golden):
+    """Backward parity at full depth: every backbone gradient of the teacher-forced train step
+    against the SAME graph evaluated by the materialising oracle in fp64 on the device (the
+    closest thing to the exact gradient).  Ours must be at least as close to it as a plain
+    fp32 evaluation of the reference algorithm (oracle in fp32) is, up to a factor 3 (at most two
+    parameters may sit outside that because of an isolated near-tie), and within 2e-2 in
+    relative L2 outright."""
+    from hspose_b200 import gcn3d
+    from hspose_b200.HSPose import control_loss
+    from hspose_b200.losses import fs_net_loss, get_gt_v
+    from oracle import torch_oracle as to
+    g = golden("e2e_train")
+    F = _flags()
+    saved = {n: getattr(F, n) for n in ("aug_pc_pro", "aug_rt_pro", "aug_bb_pro", "aug_bc_pro")}
+    for n in saved:
+        setattr(F, n, 0.0)
+    try:
+        net = _train_module(cuda)
+        batch = {k: v.to(cuda) for k, v in synth_batch(4, 1028, seed=2, train=True).items()}
+        rf = [torch.from_numpy(g[f"rf{i}"].astype(np.int64)).to(cuda) for i in range(4)]
+        torch.manual_seed(99)
+        with gcn3d.force_rf_indices(rf):
+            _, losses = net(**batch, do_loss=True)
+        sum(v.reshape(()) for v in losses["fsnet_loss"].values()).backward()
+        mine = {n: p.grad.double().cpu().numpy() for n, p in net.named_parameters() if p.grad is not None}
+        torch.manual_seed(99)
+        samples = (torch.randperm(1028)[:257].to(cuda), torch.randperm(257)[:64].to(cuda))
+
+        def oracle(dtype):
+            sd = {}
+            for name, t in net.state_dict().items():
+                t = t.detach().clone()
+                if t.is_floating_point():
+                    t = t.to(dtype)
+                    if name.rsplit(".", 1)[-1] not in ("running_mean", "running_var"):
+                        t.requires_grad_(True)
+                sd[name] = t
+            b = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in batch.items()}
+            out = to.posenet9d(sd, b["PC"], b["obj_id"], k=20, S=7, train=True, bn_training=True,
+                               samples=samples, rf_indices=rf)
+            green, red = get_gt_v(b["gt_R"])
+            pred = {"Rot1": out["p_green_R"], "Rot1_f": out["f_green_R"], "Rot2": out["p_red_R"],
+                    "Rot2_f": out["f_red_R"], "Recon": out["recon"], "Tran": out["Pred_T"],
+                    "Size": out["Pred_s"]}
+            gt = {"Rot1": green, "Rot2": red, "Recon": b["PC"], "Tran": b["gt_t"], "Size": b["gt_s"]}
+            ls = fs_net_loss()(control_loss("PoseNet_only")[0], pred, gt, b["sym"])
+            sum(v.reshape(()) for v in ls.values()).backward()
+            return {n: t.grad.double().cpu().numpy() for n, t in sd.items()
+                    if t.is_floating_point() and t.grad is not None}
+
+        g64, g32 = oracle(torch.float64), oracle(torch.float32)
+        checked = loose = 0
+        for n, ref in g64.items():
+            if "face_recon.conv_" not in n and "face_recon.bn" not in n:
+                continue
+            nr = np.linalg.norm(ref)
+            if nr < 1e-3:
+                continue
+            e_mine = np.linalg.norm(mine["posenet." + n[len("posenet."):]] - ref) / nr
+            e_f32 = np.linalg.norm(g32[n] - ref) / nr
+            assert e_mine < 2e-2, (n, e_mine, e_f32)
+            loose += e_mine > max(3 * e_f32, 5e-3)   # a near-tie decided differently: isolated
+            checked += 1
+        assert checked >= 20 and loose <= 2, (checked, loose)
     finally:
         for n, v in saved.items():
             setattr(F, n, v)
