@@ -17,7 +17,7 @@ SIGNATURES = {
     "hsp_knn_feat_workspace_bytes": (c_size_t, [c_int, c_int]),
     "hsp_knn_feat": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_size_t, P]),
     "hsp_neighbor_direction_norm": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
-    "hsp_surface_conv_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "hsp_surface_conv_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "hsp_surface_conv_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
     "hsp_surface_conv_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P,
                                      c_size_t, P]),

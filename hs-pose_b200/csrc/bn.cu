@@ -134,39 +134,45 @@ bn_reduce_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, int
   }
 }
 
-// Fixed-order sum of the per-CTA partials of 32 channels: block (32, 8), row group ry takes
-// chunks ry, ry+8, ...; the 8 group sums are then added in order 0..7 (deterministic).
-__device__ __forceinline__ void bn_sum_partials(const float* __restrict__ partial, int rchunks,
-                                                int C, int c, double& s, double& q) {
-  __shared__ double sh[2][8][32];
+// Fixed-order sum of the per-CTA partials: one CTA of 256 threads owns BN_FC = 8 channels,
+// thread (cx = tid % 8, ry = tid / 8) adds chunks ry, ry+32, ... (independent loads, all in
+// flight at once), then the 32 group sums are added in order 0..31 by the ry == 0 threads
+// (deterministic).  C/8 CTAs: wide enough that the finalize costs a few microseconds.
+constexpr int BN_FC = 8, BN_FG = 32;
+__device__ __forceinline__ bool bn_sum_partials(const float* __restrict__ partial, int rchunks,
+                                                int C, int& c, double& s, double& q) {
+  __shared__ double sh[2][BN_FG][BN_FC];
+  const int cx = threadIdx.x % BN_FC, ry = threadIdx.x / BN_FC;
+  c = blockIdx.x * BN_FC + cx;
   double a = 0.0, b = 0.0;
   if (c < C) {
-    for (int r = threadIdx.y; r < rchunks; r += 8) {
-      a += (double)partial[((size_t)r * 2) * C + c];
-      b += (double)partial[((size_t)r * 2 + 1) * C + c];
+#pragma unroll 8
+    for (int r = ry; r < rchunks; r += BN_FG) {
+      a += (double)__ldg(partial + ((size_t)r * 2) * C + c);
+      b += (double)__ldg(partial + ((size_t)r * 2 + 1) * C + c);
     }
   }
-  sh[0][threadIdx.y][threadIdx.x] = a;
-  sh[1][threadIdx.y][threadIdx.x] = b;
+  sh[0][ry][cx] = a;
+  sh[1][ry][cx] = b;
   __syncthreads();
   s = 0.0; q = 0.0;
-  if (threadIdx.y == 0) {
+  if (ry != 0 || c >= C) return false;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) { s += sh[0][g][threadIdx.x]; q += sh[1][g][threadIdx.x]; }
-  }
+  for (int g = 0; g < BN_FG; ++g) { s += sh[0][g][cx]; q += sh[1][g][cx]; }
+  return true;
 }
 
 // Forward finalize: mean / invstd, fused affine (scale, shift), running-stat update.
-__global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int rchunks, int M, int C,
-                                       float eps, float momentum, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, float* __restrict__ mean,
-                                       float* __restrict__ invstd, float* __restrict__ scale,
-                                       float* __restrict__ shift, float* __restrict__ running_mean,
-                                       float* __restrict__ running_var) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
+__global__ void __launch_bounds__(BN_FC * BN_FG)
+bn_finalize_fwd_kernel(const float* __restrict__ partial, int rchunks, int M, int C,
+                       float eps, float momentum, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float* __restrict__ mean,
+                       float* __restrict__ invstd, float* __restrict__ scale,
+                       float* __restrict__ shift, float* __restrict__ running_mean,
+                       float* __restrict__ running_var) {
+  int c;
   double s, q;
-  bn_sum_partials(partial, rchunks, C, c, s, q);
-  if (threadIdx.y != 0 || c >= C) return;
+  if (!bn_sum_partials(partial, rchunks, C, c, s, q)) return;
   const double m = s / M;
   double var = q / M - m * m;
   if (var < 0.0) var = 0.0;
@@ -184,12 +190,12 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int rc
 }
 
 // Backward finalize: dgamma = sum dy' xhat, dbeta = sum dy'.
-__global__ void bn_finalize_bwd_kernel(const float* __restrict__ partial, int rchunks, int C,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
+__global__ void __launch_bounds__(BN_FC * BN_FG)
+bn_finalize_bwd_kernel(const float* __restrict__ partial, int rchunks, int C,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  int c;
   double s, q;
-  bn_sum_partials(partial, rchunks, C, c, s, q);
-  if (threadIdx.y != 0 || c >= C) return;
+  if (!bn_sum_partials(partial, rchunks, C, c, s, q)) return;
   dbeta[c] = (float)s;
   dgamma[c] = (float)q;
 }
@@ -293,7 +299,7 @@ extern "C" int hsp_bn_relu_fwd(const void* x, int ldx, int M, int C, int dtype, 
     bn_reduce_kernel<float, 0><<<grid, BN_THREADS, 0, st>>>(
         (const float*)x, ldx, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, M, C, g.ct, part);
   HSP_LAUNCH_CHECK();
-  bn_finalize_fwd_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(part, g.rchunks, M, C, eps, momentum, gamma,
+  bn_finalize_fwd_kernel<<<(C + BN_FC - 1) / BN_FC, BN_FC * BN_FG, 0, st>>>(part, g.rchunks, M, C, eps, momentum, gamma,
                                                           beta, mean, invstd, scale, shift,
                                                           running_mean, running_var);
   HSP_LAUNCH_CHECK();
@@ -329,7 +335,7 @@ extern "C" int hsp_bn_relu_bwd(const void* x, int ldx, const void* dy, int lddy,
                                                             lddy, mean, invstd, gamma, beta, relu, M,
                                                             C, g.ct, part);
   HSP_LAUNCH_CHECK();
-  bn_finalize_bwd_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(part, g.rchunks, C, dgamma, dbeta);
+  bn_finalize_bwd_kernel<<<(C + BN_FC - 1) / BN_FC, BN_FC * BN_FG, 0, st>>>(part, g.rchunks, C, dgamma, dbeta);
   HSP_LAUNCH_CHECK();
   if (dtype == HSP_DTYPE_BF16)
     bn_bwd_apply_kernel<__nv_bfloat16><<<grid, BN_THREADS, 0, st>>>(

@@ -59,7 +59,7 @@ template <int S>
 __global__ void __launch_bounds__(GC_THREADS)
 surface_conv_fwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
                         const float* __restrict__ dirn, int N, int k, int C,
-                        float* __restrict__ out) {
+                        float* __restrict__ out, uint8_t* __restrict__ argmax) {
   __shared__ int s_idx[GC_PT * GC_MAXK];
   __shared__ float s_r[GC_PT * GC_MAXK * 3];
   const int b = blockIdx.y, i0 = blockIdx.x * GC_PT;
@@ -80,19 +80,37 @@ surface_conv_fwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict
   if (c >= C) return;
   for (int p = 0; p < npts; ++p) {
     float acc[S];
+    int am[S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) acc[s] = 0.0f;  // max_n relu(x_n) = max(0, max_n x_n)
-    for (int n = 0; n < k; ++n) {
-      const float rx = s_r[3 * (p * k + n)], ry = s_r[3 * (p * k + n) + 1],
-                  rz = s_r[3 * (p * k + n) + 2];
+    for (int s = 0; s < S; ++s) { acc[s] = 0.0f; am[s] = 255; }  // max_n relu(x_n) = max(0, max_n x_n)
+    if (argmax) {
+      for (int n = 0; n < k; ++n) {
+        const float rx = s_r[3 * (p * k + n)], ry = s_r[3 * (p * k + n) + 1],
+                    rz = s_r[3 * (p * k + n) + 2];
 #pragma unroll
-      for (int s = 0; s < S; ++s)
-        acc[s] = fmaxf(acc[s], fmaf(rz, dz[s], fmaf(ry, dy[s], rx * dx[s])));
+        for (int s = 0; s < S; ++s) {
+          const float th = fmaf(rz, dz[s], fmaf(ry, dy[s], rx * dx[s]));
+          if (th > acc[s]) { acc[s] = th; am[s] = n; }
+        }
+      }
+    } else {
+      for (int n = 0; n < k; ++n) {
+        const float rx = s_r[3 * (p * k + n)], ry = s_r[3 * (p * k + n) + 1],
+                    rz = s_r[3 * (p * k + n) + 2];
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          acc[s] = fmaxf(acc[s], fmaf(rz, dz[s], fmaf(ry, dy[s], rx * dx[s])));
+      }
     }
     float sum = 0.0f;
 #pragma unroll
     for (int s = 0; s < S; ++s) sum += acc[s];
-    out[((size_t)b * N + i0 + p) * C + c] = __fdiv_rn(sum, (float)S);
+    const size_t row = (size_t)b * N + i0 + p;
+    out[row * C + c] = __fdiv_rn(sum, (float)S);
+    if (argmax) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) argmax[row * SC + s * C + c] = (uint8_t)am[s];
+    }
   }
 }
 
@@ -330,24 +348,16 @@ constexpr int GC_BWD_CTAS = 148 * 4;
 template <int S>
 __global__ void __launch_bounds__(GC_THREADS)
 surface_conv_bwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
-                        const float* __restrict__ dirn, const float* __restrict__ gout, int B,
+                        const uint8_t* __restrict__ argmax, const float* __restrict__ gout, int B,
                         int N, int k, int C, float* __restrict__ partial) {
   __shared__ int s_idx[GC_PT * GC_MAXK];
   __shared__ float s_r[GC_PT * GC_MAXK * 3];
   const int c = blockIdx.z * GC_THREADS + threadIdx.x;
   const int SC = S * C;
   const int tiles = (N + GC_PT - 1) / GC_PT;
-  float dx[S], dy[S], dz[S], gx[S], gy[S], gz[S];
+  float gx[S], gy[S], gz[S];
 #pragma unroll
-  for (int s = 0; s < S; ++s) {
-    gx[s] = gy[s] = gz[s] = 0.0f;
-    dx[s] = dy[s] = dz[s] = 0.0f;
-    if (c < C) {
-      dx[s] = dirn[s * C + c];
-      dy[s] = dirn[SC + s * C + c];
-      dz[s] = dirn[2 * SC + s * C + c];
-    }
-  }
+  for (int s = 0; s < S; ++s) gx[s] = gy[s] = gz[s] = 0.0f;
   for (int w = blockIdx.x; w < B * tiles; w += gridDim.x) {
     const int b = w / tiles, i0 = (w % tiles) * GC_PT;
     const int npts = min(GC_PT, N - i0);
@@ -356,24 +366,13 @@ surface_conv_bwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict
     __syncthreads();
     if (c < C) {
       for (int p = 0; p < npts; ++p) {
-        float acc[S];
-        int am[S];
-#pragma unroll
-        for (int s = 0; s < S; ++s) { acc[s] = 0.0f; am[s] = -1; }
-        for (int n = 0; n < k; ++n) {
-          const float rx = s_r[3 * (p * k + n)], ry = s_r[3 * (p * k + n) + 1],
-                      rz = s_r[3 * (p * k + n) + 2];
-#pragma unroll
-          for (int s = 0; s < S; ++s) {
-            float th = fmaf(rz, dz[s], fmaf(ry, dy[s], rx * dx[s]));
-            if (th > acc[s]) { acc[s] = th; am[s] = n; }
-          }
-        }
-        const float gs = __fdiv_rn(gout[((size_t)b * N + i0 + p) * C + c], (float)S);
+        const size_t row = (size_t)b * N + i0 + p;
+        const float gs = __fdiv_rn(gout[row * C + c], (float)S);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-          if (am[s] >= 0) {
-            const float* r = s_r + 3 * (p * k + am[s]);
+          const int n = argmax[row * SC + s * C + c];   // 255: relu killed every neighbour
+          if (n < k) {
+            const float* r = s_r + 3 * (p * k + n);
             gx[s] = fmaf(gs, r[0], gx[s]);
             gy[s] = fmaf(gs, r[1], gy[s]);
             gz[s] = fmaf(gs, r[2], gz[s]);
@@ -492,13 +491,13 @@ static bool bad_dims(int B, int N, int k, int S, int C) {
 
 extern "C" int hsp_surface_conv_fwd(const float* xyz, const int32_t* idx, const float* dirn,
                                     int B, int N, int k, int S, int C, float* out,
-                                    void* stream) {
+                                    uint8_t* argmax, void* stream) {
   using namespace hsp;
   if (!xyz || !idx || !dirn || !out || bad_dims(B, N, k, S, C)) return HSP_EINVAL;
   if (B == 0) return HSP_OK;
   dim3 grid((N + GC_PT - 1) / GC_PT, B, (C + GC_THREADS - 1) / GC_THREADS);
   cudaStream_t st = (cudaStream_t)stream;
-  HSP_DISPATCH_S(S, (surface_conv_fwd_kernel<S><<<grid, GC_THREADS, 0, st>>>(xyz, idx, dirn, N, k, C, out)));
+  HSP_DISPATCH_S(S, (surface_conv_fwd_kernel<S><<<grid, GC_THREADS, 0, st>>>(xyz, idx, dirn, N, k, C, out, argmax)));
   HSP_LAUNCH_CHECK();
   return HSP_OK;
 }
@@ -545,12 +544,12 @@ extern "C" size_t hsp_graph_conv_bwd_workspace_bytes(int B, int N, int k, int S,
   return hsp_surface_conv_bwd_workspace_bytes(B, N, k, S, C);
 }
 
-extern "C" int hsp_surface_conv_bwd(const float* xyz, const int32_t* idx, const float* dirn,
+extern "C" int hsp_surface_conv_bwd(const float* xyz, const int32_t* idx, const uint8_t* argmax,
                                     const float* gout, int B, int N, int k, int S, int C,
                                     float* gdirn, void* workspace, size_t workspace_bytes,
                                     void* stream) {
   using namespace hsp;
-  if (!xyz || !idx || !dirn || !gout || !gdirn || bad_dims(B, N, k, S, C)) return HSP_EINVAL;
+  if (!xyz || !idx || !argmax || !gout || !gdirn || bad_dims(B, N, k, S, C)) return HSP_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   if (B == 0) {
     return cudaMemsetAsync(gdirn, 0, sizeof(float) * 3 * S * C, st) == cudaSuccess ? HSP_OK
@@ -561,7 +560,7 @@ extern "C" int hsp_surface_conv_bwd(const float* xyz, const int32_t* idx, const 
   const int ctas = bwd_ctas(B, N);
   dim3 grid(ctas, 1, (C + GC_THREADS - 1) / GC_THREADS);
   HSP_DISPATCH_S(S, (surface_conv_bwd_kernel<S><<<grid, GC_THREADS, 0, st>>>(
-                        xyz, idx, dirn, gout, B, N, k, C, (float*)workspace)));
+                        xyz, idx, argmax, gout, B, N, k, C, (float*)workspace)));
   HSP_LAUNCH_CHECK();
   const int cols = 3 * S * C;
   dir_reduce_kernel<<<(cols + 127) / 128, 128, 0, st>>>((const float*)workspace, ctas, cols, gdirn);

@@ -130,25 +130,28 @@ class _SurfaceConv(torch.autograd.Function):
         idx32 = _need(idx32, torch.int32, "idx")
         dirn = _need(dirn, torch.float32, "dirn")
         B, N, k = idx32.shape
+        need_grad = ctx.needs_input_grad[2]
         with torch.cuda.device(xyz.device):
             out = torch.empty(B, N, C, dtype=torch.float32, device=xyz.device)
+            am = torch.empty(B, N, S * C, dtype=torch.uint8, device=xyz.device) if need_grad else None
             _call("hsp_surface_conv_fwd", _p(xyz), _p(idx32), _p(dirn), B, N, k, S, C, _p(out),
-                  _stream())
-        ctx.save_for_backward(xyz, idx32, dirn)
+                  _p(am), _stream())
+        if need_grad:
+            ctx.save_for_backward(xyz, idx32, am)
         ctx.dims = (B, N, k, S, C)
         return out
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gout):
-        xyz, idx32, dirn = ctx.saved_tensors
+        xyz, idx32, am = ctx.saved_tensors
         B, N, k, S, C = ctx.dims
         gout = _need(gout.float(), torch.float32, "gout")
         with torch.cuda.device(xyz.device):
             lib = _lib.load()
             ws = _workspace(lib.hsp_surface_conv_bwd_workspace_bytes(B, N, k, S, C), xyz.device)
-            gdirn = torch.empty_like(dirn)
-            _call("hsp_surface_conv_bwd", _p(xyz), _p(idx32), _p(dirn), _p(gout), B, N, k, S, C,
+            gdirn = torch.empty(3, S * C, dtype=torch.float32, device=xyz.device)
+            _call("hsp_surface_conv_bwd", _p(xyz), _p(idx32), _p(am), _p(gout), B, N, k, S, C,
                   _p(gdirn), _p(ws), ws.numel(), _stream())
         return None, None, gdirn, None, None
 

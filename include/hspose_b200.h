@@ -86,11 +86,15 @@ int hsp_neighbor_direction_norm(const float* xyz, const int32_t* idx, int B, int
  * in-kernel.  xyz (B,N,3); idx (B,N,k) int32; dirn (3,S*C) already
  * column-normalised (F.normalize(directions, dim=0)); out (B,N,C).         */
 int hsp_surface_conv_fwd(const float* xyz, const int32_t* idx, const float* dirn,
-                         int B, int N, int k, int S, int C, float* out, void* stream);
-/* grad wrt dirn: gdirn (3,S*C) (overwritten).  Deterministic two-stage
- * reduction through `workspace`.                                           */
+                         int B, int N, int k, int S, int C, float* out, uint8_t* argmax,
+                         void* stream);
+/* argmax (B,N,S*C) uint8, optional (NULL when no gradient is needed): the
+ * neighbour slot that won max_n, 255 when ReLU zeroed every neighbour.
+ * grad wrt dirn: gdirn (3,S*C) (overwritten) replays only the winners
+ * (N*S*C work instead of N*k*S*C).  Deterministic two-stage reduction through
+ * `workspace`.                                                             */
 size_t hsp_surface_conv_bwd_workspace_bytes(int B, int N, int k, int S, int C);
-int hsp_surface_conv_bwd(const float* xyz, const int32_t* idx, const float* dirn,
+int hsp_surface_conv_bwd(const float* xyz, const int32_t* idx, const uint8_t* argmax,
                          const float* gout, int B, int N, int k, int S, int C,
                          float* gdirn, void* workspace, size_t workspace_bytes,
                          void* stream);
