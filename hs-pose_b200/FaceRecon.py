@@ -55,6 +55,25 @@ def conv1x1(conv: nn.Conv1d, x_bnc, pad_in=0, pad_out=0):
     return F.linear(x_bnc, w, b)
 
 
+def conv_bn_relu_points(conv: nn.Conv1d, bn: nn.BatchNorm1d, x_bnc, relu=True):
+    """Conv1d(k=1) -> BatchNorm1d -> ReLU on a (bs, N, C) / (M, C) tensor.  On the mixed-precision
+    training path this is ONE fused autograd node (ops.linear_bn_relu: bf16 tensor-core GEMMs,
+    K6b BN kernels, bias gradient from the BN backward); otherwise the three modules in turn."""
+    shape = x_bnc.shape
+    pad_in = shape[-1] - conv.in_channels
+    if (bn.training and mixed_precision() and x_bnc.is_cuda and conv.out_channels % 8 == 0
+            and shape[-1] % 8 == 0 and x_bnc.numel() // shape[-1] > 1):
+        w = conv.weight[:, :, 0]
+        if pad_in:
+            w = F.pad(w, (0, pad_in))
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        z = ops.linear_bn_relu(x_bnc.reshape(-1, shape[-1]), w, conv.bias, bn.weight, bn.bias,
+                               bn.running_mean, bn.running_var, bn.eps, bn.momentum, relu)
+        return z.view(*shape[:-1], conv.out_channels)
+    return bn_points(bn, conv1x1(conv, x_bnc, pad_in), relu=relu)
+
+
 def seq_points(seq: nn.Sequential, x_bnc):
     """Run a Conv1d/BatchNorm1d/ReLU nn.Sequential (FaceRecon.py:38-68) in (bs, N, C) layout;
     BN+ReLU pairs are fused; a narrow last conv (3 / 30 channels) is computed 8-aligned."""
@@ -62,6 +81,11 @@ def seq_points(seq: nn.Sequential, x_bnc):
     i = 0
     while i < len(mods):
         m = mods[i]
+        if (isinstance(m, nn.Conv1d) and i + 2 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d)
+                and isinstance(mods[i + 2], nn.ReLU)):
+            x_bnc = conv_bn_relu_points(m, mods[i + 1], x_bnc, relu=True)
+            i += 3
+            continue
         if isinstance(m, nn.Conv1d):
             pad_in = x_bnc.shape[-1] - m.in_channels
             pad_out = (-m.out_channels) % 8 if mixed_precision() else 0

@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .FaceRecon import bn_points, conv1x1
+from .FaceRecon import conv_bn_relu_points
 from .flags import FLAGS
 
 
@@ -29,8 +29,8 @@ class _PointHead(nn.Module):
 
     def forward_points(self, x_bnc):
         # x_bnc may be the 16-aligned padded feature buffer (extra columns get zero weights)
-        x = bn_points(self.bn1, conv1x1(self.conv1, x_bnc, pad_in=x_bnc.shape[-1] - self.f), relu=True)
-        x = bn_points(self.bn2, conv1x1(self.conv2, x), relu=True)
+        x = conv_bn_relu_points(self.conv1, self.bn1, x_bnc)
+        x = conv_bn_relu_points(self.conv2, self.bn2, x)
         x = torch.max(x, 1)[0]                                  # (bs, 256): max over points
         x = F.relu(self.bn3(F.linear(x, self.conv3.weight[:, :, 0], self.conv3.bias)))
         x = self.drop1(x)

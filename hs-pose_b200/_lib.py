@@ -36,7 +36,7 @@ SIGNATURES = {
     "hsp_bn_relu_fwd": (c_int, [P, c_int, c_int, c_int, c_int, P, P, ctypes.c_float, ctypes.c_float,
                                 c_int, P, P, P, P, P, P, c_int, P, c_size_t, P]),
     "hsp_bn_relu_bwd": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, P, P, P, P, c_int, P, P, P,
-                                c_int, P, c_size_t, P]),
+                                c_int, P, P, c_size_t, P]),
     "hsp_chamfer_fwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P, P]),
     "hsp_chamfer_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, P]),
 }

@@ -35,6 +35,10 @@ template <> struct Vec8<float> {
     reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
     reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
   }
+  static __device__ __forceinline__ void round(const float* v, float* r) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = v[i];
+  }
 };
 template <> struct Vec8<__nv_bfloat16> {
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
@@ -52,6 +56,10 @@ template <> struct Vec8<__nv_bfloat16> {
 #pragma unroll
     for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
     *reinterpret_cast<uint4*>(p) = u;
+  }
+  static __device__ __forceinline__ void round(const float* v, float* r) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
   }
 };
 
@@ -234,7 +242,9 @@ bn_bwd_apply_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, 
                     const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta,
                     const float* __restrict__ dgamma, const float* __restrict__ dbeta, int relu,
-                    int M, int C, int ct, T* __restrict__ dx, int lddx) {
+                    int M, int C, int ct, T* __restrict__ dx, int lddx,
+                    float* __restrict__ colsum_partial) {
+  __shared__ float s_cs[BN_THREADS * BN_VEC];
   const int rl = BN_THREADS / ct;
   const int col = threadIdx.x % ct, rlane = threadIdx.x / ct;
   const int c0 = (blockIdx.x * ct + col) * BN_VEC;
@@ -246,6 +256,9 @@ bn_bwd_apply_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, 
     ga[i] = gamma ? gamma[c0 + i] : 1.f; be[i] = beta ? beta[c0 + i] : 0.f;
     k1[i] = dbeta[c0 + i] * invM; k2[i] = dgamma[c0 + i] * invM;
   }
+  float cs[BN_VEC];
+#pragma unroll
+  for (int i = 0; i < BN_VEC; ++i) cs[i] = 0.f;
   const int rows_per = (M + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
 #pragma unroll 2
@@ -260,6 +273,25 @@ bn_bwd_apply_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, 
       xv[i] = ga[i] * is[i] * (g - k1[i] - xh * k2[i]);
     }
     Vec8<T>::store(dx + (size_t)r * lddx + c0, xv);
+    if (colsum_partial) {   // column sums of dx AS STORED (rounded to T): the bias gradient
+      float rv[BN_VEC];     // of the Linear in front of this BatchNorm (= sum_rows dY)
+      Vec8<T>::round(xv, rv);
+#pragma unroll
+      for (int i = 0; i < BN_VEC; ++i) cs[i] += rv[i];
+    }
+  }
+  if (colsum_partial) {
+#pragma unroll
+    for (int i = 0; i < BN_VEC; ++i) s_cs[i * BN_THREADS + threadIdx.x] = cs[i];
+    __syncthreads();
+    for (int t = threadIdx.x; t < ct * BN_VEC; t += BN_THREADS) {
+      const int cc = t % ct, q = t / ct;
+      float a = 0.f;
+      for (int l = 0; l < rl; ++l) a += s_cs[q * BN_THREADS + l * ct + cc];
+      const int ch = (blockIdx.x * ct + cc) * BN_VEC + q;
+      colsum_partial[((size_t)blockIdx.y * 2) * C + ch] = a;   // same layout as bn_reduce partials
+      colsum_partial[((size_t)blockIdx.y * 2 + 1) * C + ch] = 0.f;
+    }
   }
 }
 
@@ -274,7 +306,7 @@ static bool bn_bad(const void* x, int M, int C, int ld, int dtype) {
 extern "C" size_t hsp_bn_workspace_bytes(int M, int C) {
   using namespace hsp;
   if (M <= 0 || C <= 0 || (C % BN_VEC) != 0) return 0;
-  return (size_t)bn_geom(M, C).rchunks * 2 * C * sizeof(float);
+  return ((size_t)bn_geom(M, C).rchunks * 2 * C + C) * sizeof(float);
 }
 
 extern "C" int hsp_bn_relu_fwd(const void* x, int ldx, int M, int C, int dtype, const float* gamma,
@@ -316,7 +348,8 @@ extern "C" int hsp_bn_relu_fwd(const void* x, int ldx, int M, int C, int dtype, 
 extern "C" int hsp_bn_relu_bwd(const void* x, int ldx, const void* dy, int lddy, int M, int C,
                                int dtype, const float* gamma, const float* beta, const float* mean,
                                const float* invstd, int relu, float* dgamma, float* dbeta, void* dx,
-                               int lddx, void* workspace, size_t workspace_bytes, void* stream) {
+                               int lddx, float* dx_colsum, void* workspace, size_t workspace_bytes,
+                               void* stream) {
   using namespace hsp;
   if (bn_bad(x, M, C, ldx, dtype) || bn_bad(dy, M, C, lddy, dtype) || bn_bad(dx, M, C, lddx, dtype) ||
       !mean || !invstd || !dgamma || !dbeta)
@@ -340,11 +373,17 @@ extern "C" int hsp_bn_relu_bwd(const void* x, int ldx, const void* dy, int lddy,
   if (dtype == HSP_DTYPE_BF16)
     bn_bwd_apply_kernel<__nv_bfloat16><<<grid, BN_THREADS, 0, st>>>(
         (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)dy, lddy, mean, invstd, gamma, beta, dgamma,
-        dbeta, relu, M, C, g.ct, (__nv_bfloat16*)dx, lddx);
+        dbeta, relu, M, C, g.ct, (__nv_bfloat16*)dx, lddx, dx_colsum ? part : nullptr);
   else
     bn_bwd_apply_kernel<float><<<grid, BN_THREADS, 0, st>>>((const float*)x, ldx, (const float*)dy, lddy,
                                                             mean, invstd, gamma, beta, dgamma, dbeta,
-                                                            relu, M, C, g.ct, (float*)dx, lddx);
+                                                            relu, M, C, g.ct, (float*)dx, lddx,
+                                                            dx_colsum ? part : nullptr);
   HSP_LAUNCH_CHECK();
+  if (dx_colsum) {   // fixed-order sum of the per-CTA column sums (the second partial plane is zero)
+    bn_finalize_bwd_kernel<<<(C + BN_FC - 1) / BN_FC, BN_FC * BN_FG, 0, st>>>(
+        part, g.rchunks, C, (float*)workspace + (size_t)g.rchunks * 2 * C, dx_colsum);
+    HSP_LAUNCH_CHECK();
+  }
   return HSP_OK;
 }

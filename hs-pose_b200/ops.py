@@ -462,18 +462,9 @@ class _BnRelu(torch.autograd.Function):
             raise _lib.HSPoseLibraryError("bn_relu: expected a CUDA (M,C) matrix with unit column stride")
         if x.dtype not in (torch.float32, torch.bfloat16):
             raise TypeError(f"bn_relu: unsupported dtype {x.dtype}")
-        M, C = x.shape
-        dt = BF16 if x.dtype == torch.bfloat16 else F32
         gamma = gamma.float().contiguous()
         beta = beta.float().contiguous()
-        lib = _lib.load()
-        with torch.cuda.device(x.device):
-            y = torch.empty(M, C, dtype=x.dtype, device=x.device)
-            stats = torch.empty(4, C, dtype=torch.float32, device=x.device)  # mean, invstd, scale, shift
-            ws = _workspace(lib.hsp_bn_workspace_bytes(M, C), x.device)
-            _call("hsp_bn_relu_fwd", _p(x), x.stride(0), M, C, dt, _p(gamma), _p(beta), float(eps),
-                  float(momentum), int(relu), _p(running_mean), _p(running_var), _p(stats[0]),
-                  _p(stats[1]), _p(stats[2]), _p(y), C, _p(ws), ws.numel(), _stream())
+        y, stats = _bn_fwd_raw(x, gamma, beta, running_mean, running_var, eps, momentum, relu)
         ctx.save_for_backward(x, gamma, beta, stats)
         ctx.relu = int(relu)
         return y
@@ -481,25 +472,83 @@ class _BnRelu(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, gamma, beta, stats = ctx.saved_tensors
-        M, C = x.shape
-        dt = BF16 if x.dtype == torch.bfloat16 else F32
-        dy = dy.to(x.dtype)
-        if dy.stride(1) != 1 or (dy.stride(0) * dy.element_size()) % 16 != 0:
-            dy = dy.contiguous()
-        lib = _lib.load()
-        with torch.cuda.device(x.device):
-            dx = torch.empty(M, C, dtype=x.dtype, device=x.device)
-            dgb = torch.empty(2, C, dtype=torch.float32, device=x.device)
-            ws = _workspace(lib.hsp_bn_workspace_bytes(M, C), x.device)
-            _call("hsp_bn_relu_bwd", _p(x), x.stride(0), _p(dy), dy.stride(0), M, C, dt, _p(gamma),
-                  _p(beta), _p(stats[0]), _p(stats[1]), ctx.relu, _p(dgb[0]), _p(dgb[1]), _p(dx), C,
-                  _p(ws), ws.numel(), _stream())
-        return dx, dgb[0], dgb[1], None, None, None, None, None
+        dx, dgamma, dbeta, _ = _bn_bwd_raw(x, dy, gamma, beta, stats, ctx.relu, False)
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
+def _bn_fwd_raw(x, gamma, beta, running_mean, running_var, eps, momentum, relu):
+    """x (M,C) unit column stride -> (y (M,C) contiguous, stats (4,C) = mean, invstd, scale, shift)."""
+    M, C = x.shape
+    dt = BF16 if x.dtype == torch.bfloat16 else F32
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        y = torch.empty(M, C, dtype=x.dtype, device=x.device)
+        stats = torch.empty(4, C, dtype=torch.float32, device=x.device)
+        ws = _workspace(lib.hsp_bn_workspace_bytes(M, C), x.device)
+        _call("hsp_bn_relu_fwd", _p(x), x.stride(0), M, C, dt, _p(gamma), _p(beta), float(eps),
+              float(momentum), int(relu), _p(running_mean), _p(running_var), _p(stats[0]),
+              _p(stats[1]), _p(stats[2]), _p(y), C, _p(ws), ws.numel(), _stream())
+    return y, stats
+
+
+def _bn_bwd_raw(x, dy, gamma, beta, stats, relu, want_colsum):
+    """-> (dx, dgamma, dbeta, colsum(dx) | None)."""
+    M, C = x.shape
+    dt = BF16 if x.dtype == torch.bfloat16 else F32
+    dy = dy.to(x.dtype)
+    if dy.stride(1) != 1 or (dy.stride(0) * dy.element_size()) % 16 != 0:
+        dy = dy.contiguous()
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        dx = torch.empty(M, C, dtype=x.dtype, device=x.device)
+        dgb = torch.empty(3, C, dtype=torch.float32, device=x.device)
+        ws = _workspace(lib.hsp_bn_workspace_bytes(M, C), x.device)
+        _call("hsp_bn_relu_bwd", _p(x), x.stride(0), _p(dy), dy.stride(0), M, C, dt, _p(gamma),
+              _p(beta), _p(stats[0]), _p(stats[1]), int(relu), _p(dgb[0]), _p(dgb[1]), _p(dx), C,
+              _p(dgb[2]) if want_colsum else None, _p(ws), ws.numel(), _stream())
+    if want_colsum:
+        global _launches
+        _launches += 1   # the column-sum finalize
+    return dx, dgb[0], dgb[1], (dgb[2] if want_colsum else None)
 
 
 def bn_relu(x, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, relu=True):
     """y = relu?(batchnorm_train(x)) over the rows of the (M,C) matrix x."""
     return _BnRelu.apply(x, gamma, beta, running_mean, running_var, eps, momentum, relu)
+
+
+class _LinearBnRelu(torch.autograd.Function):
+    """z = relu?(batchnorm_train(x @ W^T + b)) over the rows of x (M,K) — one Conv1d(k=1) ->
+    BatchNorm1d -> ReLU block of the dense per-point MLPs (reference FaceRecon.py:38-68,
+    PoseR.py:26-29, PoseTs.py:31-34) as ONE autograd node on the mixed-precision path:
+    bf16 tensor-core GEMMs (library), K6b for the BN, and the Linear's bias gradient comes out
+    of the BN-backward kernel (column sums of dY) instead of a separate reduction pass."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, gamma, beta, running_mean, running_var, eps, momentum, relu):
+        xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+        Wb = W.to(torch.bfloat16)
+        with torch.autocast("cuda", enabled=False):
+            y = torch.addmm(b.to(torch.bfloat16), xb, Wb.t()) if b is not None else xb @ Wb.t()
+        g32, b32 = gamma.float().contiguous(), beta.float().contiguous()
+        z, stats = _bn_fwd_raw(y, g32, b32, running_mean, running_var, eps, momentum, relu)
+        ctx.save_for_backward(xb, Wb, y, g32, b32, stats)
+        ctx.relu, ctx.has_bias = int(relu), b is not None
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        xb, Wb, y, g32, b32, stats = ctx.saved_tensors
+        dy, dgamma, dbeta, colsum = _bn_bwd_raw(y, dz, g32, b32, stats, ctx.relu, ctx.has_bias)
+        with torch.autocast("cuda", enabled=False):
+            dx = dy @ Wb if ctx.needs_input_grad[0] else None
+            dW = (dy.t() @ xb).float()
+        return dx, dW, colsum, dgamma, dbeta, None, None, None, None, None
+
+
+def linear_bn_relu(x, W, b, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, relu=True):
+    """Fused Linear -> BatchNorm(train) -> ReLU on a (M,K) matrix (bf16 compute)."""
+    return _LinearBnRelu.apply(x, W, b, gamma, beta, running_mean, running_var, eps, momentum, relu)
 
 
 # ---------------------------------------------------------------- chamfer

@@ -186,7 +186,9 @@ int hsp_chamfer_bwd(const float* a, const float* b, const int32_t* idx_a,
  *   fwd: mean, invstd (C each) and scale_shift (2C) are outputs kept for the
  *        backward; running_mean / running_var (may be NULL) are updated with
  *        `momentum` (unbiased variance), as nn.BatchNorm1d does.
- *   bwd: dgamma, dbeta (C each), dx.  The ReLU mask is recomputed from x.
+ *   bwd: dgamma, dbeta (C each), dx.  The ReLU mask is recomputed from x.  dx_colsum
+ *        (C, optional) receives sum_rows dx as stored — the bias gradient of the Linear /
+ *        Conv1d(k=1) that produced x, so that layer needs no separate reduction pass.
  * Deterministic (fixed-order partial sums through `workspace`).             */
 size_t hsp_bn_workspace_bytes(int M, int C);
 int hsp_bn_relu_fwd(const void* x, int ldx, int M, int C, int dtype, const float* gamma,
@@ -197,7 +199,8 @@ int hsp_bn_relu_fwd(const void* x, int ldx, int M, int C, int dtype, const float
 int hsp_bn_relu_bwd(const void* x, int ldx, const void* dy, int lddy, int M, int C, int dtype,
                     const float* gamma, const float* beta, const float* mean,
                     const float* invstd, int relu, float* dgamma, float* dbeta, void* dx,
-                    int lddx, void* workspace, size_t workspace_bytes, void* stream);
+                    int lddx, float* dx_colsum, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 #ifdef __cplusplus
 }
