@@ -52,17 +52,32 @@ __device__ __forceinline__ void warp_insert(uint64_t& L, uint64_t key, int lane)
   else if (lane > pos) L = up;
 }
 
+// Orderable key -> the float it encodes (inverse of float_orderable).
+__device__ __forceinline__ float key_to_float(uint64_t key) {
+  const uint32_t o = (uint32_t)(key >> 32);
+  return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
+
+// v2: the inner products run on the packed-FP32 datapath.  A thread owns 4 query rows x 4
+// PAIRS of adjacent candidates; the candidate chunk is staged TRANSPOSED ([d][j]) so one
+// LDS.64 yields (B[j][d], B[j+1][d]) and one FFMA2 advances two accumulators:
+//   acc2[r][c] = fma2((a,a), (b_j, b_j+1), acc2[r][c])
+// Every accumulator is still ONE sequential fp32 FMA chain over d = 0..D-1 (FFMA2 is two
+// independent IEEE fmas) — bit-identical to the scalar kernel and the oracle.
+constexpr int KF2_TC = 128;                 // candidates per tile (16 tx x 4 pairs x 2)
+constexpr int KF2_LDBT = KF2_TC + 2;        // transposed chunk pitch (8-byte aligned rows)
+constexpr int KF2_LDD = KF2_TC + 1;
+
 template <int NL>
-__global__ void __launch_bounds__(KF_THREADS)
+__global__ void __launch_bounds__(KF_THREADS, 2)
 knn_feat_kernel(const float* __restrict__ feat, const float* __restrict__ qn, int N, int D, int K,
                 int drop, int64_t* __restrict__ idx64, int32_t* __restrict__ idx32) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int LDA = D + 4;
-  float* s_A = reinterpret_cast<float*>(smem_raw);                  // [TQ][LDA]
-  float* s_B = s_A + KF_TQ * LDA;                                   // [TC][LDB]
-  float* s_D = s_B + KF_TC * KF_LDB;                                // [TQ][LDD]
-  uint64_t* s_L = reinterpret_cast<uint64_t*>(s_D + KF_TQ * KF_LDD + ((KF_TQ * KF_LDD) & 1));
-  // s_L: [TQ][NL*32]
+  float* s_A = reinterpret_cast<float*>(smem_raw);                  // [TQ][LDA]      row-major queries
+  float* s_BT = s_A + KF_TQ * LDA;                                  // [DK][LDBT]     transposed chunk
+  float* s_D = s_BT + KF_DK * KF2_LDBT;                             // [TQ][LDD]      distance tile
+  uint64_t* s_L = reinterpret_cast<uint64_t*>(s_D + KF_TQ * KF2_LDD + ((KF_TQ * KF2_LDD) & 1));
   const int b = blockIdx.y, q0 = blockIdx.x * KF_TQ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid & 15, ty = tid >> 4;
@@ -84,52 +99,60 @@ knn_feat_kernel(const float* __restrict__ feat, const float* __restrict__ qn, in
     qi[r] = i < N ? __ldg(qb + i) : 0.0f;
   }
 
-  for (int j0 = 0; j0 < N; j0 += KF_TC) {
-    float acc[KF_MQ][KF_MC];
+  for (int j0 = 0; j0 < N; j0 += KF2_TC) {
+    float2 acc[KF_MQ][4];
 #pragma unroll
     for (int r = 0; r < KF_MQ; ++r)
 #pragma unroll
-      for (int c = 0; c < KF_MC; ++c) acc[r][c] = 0.0f;
+      for (int c = 0; c < 4; ++c) acc[r][c] = make_float2(0.0f, 0.0f);
 
     for (int d0 = 0; d0 < D; d0 += KF_DK) {
-      __syncthreads();  // previous chunk / previous tile's selection done with s_B / s_D
-      for (int e = tid; e < KF_TC * (KF_DK / 4); e += KF_THREADS) {
+      __syncthreads();  // previous chunk / previous tile's selection done with s_BT / s_D
+      // stage the chunk transposed: lanes walk d fastest (coalesced 128-byte row pieces)
+      for (int e = tid; e < KF2_TC * (KF_DK / 4); e += KF_THREADS) {
         const int r = e / (KF_DK / 4), d4 = e % (KF_DK / 4);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j0 + r < N)
           v = __ldg(reinterpret_cast<const float4*>(fb + (size_t)(j0 + r) * D + d0) + d4);
-        *reinterpret_cast<float4*>(s_B + r * KF_LDB + 4 * d4) = v;
+        float* dst = s_BT + (4 * d4) * KF2_LDBT + r;
+        dst[0] = v.x; dst[KF2_LDBT] = v.y; dst[2 * KF2_LDBT] = v.z; dst[3 * KF2_LDBT] = v.w;
       }
       __syncthreads();
 #pragma unroll
       for (int d4 = 0; d4 < KF_DK / 4; ++d4) {
-        float4 a[KF_MQ], bb[KF_MC];
+        float4 a[KF_MQ];
 #pragma unroll
         for (int r = 0; r < KF_MQ; ++r)
           a[r] = *reinterpret_cast<const float4*>(s_A + (ty + 16 * r) * LDA + d0 + 4 * d4);
 #pragma unroll
-        for (int c = 0; c < KF_MC; ++c)
-          bb[c] = *reinterpret_cast<const float4*>(s_B + (tx + 16 * c) * KF_LDB + 4 * d4);
+        for (int dd = 0; dd < 4; ++dd) {
+          float2 bb[4];
 #pragma unroll
-        for (int r = 0; r < KF_MQ; ++r)
+          for (int c = 0; c < 4; ++c)
+            bb[c] = *reinterpret_cast<const float2*>(s_BT + (4 * d4 + dd) * KF2_LDBT + 2 * tx + 32 * c);
 #pragma unroll
-          for (int c = 0; c < KF_MC; ++c) {
-            acc[r][c] = __fmaf_rn(a[r].x, bb[c].x, acc[r][c]);
-            acc[r][c] = __fmaf_rn(a[r].y, bb[c].y, acc[r][c]);
-            acc[r][c] = __fmaf_rn(a[r].z, bb[c].z, acc[r][c]);
-            acc[r][c] = __fmaf_rn(a[r].w, bb[c].w, acc[r][c]);
+          for (int r = 0; r < KF_MQ; ++r) {
+            const float av = dd == 0 ? a[r].x : dd == 1 ? a[r].y : dd == 2 ? a[r].z : a[r].w;
+            const float2 a2 = make_float2(av, av);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = __ffma2_rn(a2, bb[c], acc[r][c]);
           }
+        }
       }
     }
     // distance tile: ((-2*inner) + q_j) + q_i        (gcn3d.py:21)
 #pragma unroll
-    for (int c = 0; c < KF_MC; ++c) {
-      const int j = j0 + tx + 16 * c;
-      const float qj = j < N ? __ldg(qb + j) : 0.0f;
+    for (int c = 0; c < 4; ++c) {
+      const int jl = 2 * tx + 32 * c;
+      const int j = j0 + jl;
+      const float qj0 = j < N ? __ldg(qb + j) : 0.0f;
+      const float qj1 = j + 1 < N ? __ldg(qb + j + 1) : 0.0f;
 #pragma unroll
-      for (int r = 0; r < KF_MQ; ++r)
-        s_D[(ty + 16 * r) * KF_LDD + tx + 16 * c] =
-            __fadd_rn(__fadd_rn(__fmul_rn(acc[r][c], -2.0f), qj), qi[r]);
+      for (int r = 0; r < KF_MQ; ++r) {
+        float* dst = s_D + (ty + 16 * r) * KF2_LDD + jl;
+        dst[0] = __fadd_rn(__fadd_rn(__fmul_rn(acc[r][c].x, -2.0f), qj0), qi[r]);
+        dst[1] = __fadd_rn(__fadd_rn(__fmul_rn(acc[r][c].y, -2.0f), qj1), qi[r]);
+      }
     }
     __syncthreads();
     // selection: warp w owns rows w, w+8, ...
@@ -139,12 +162,16 @@ knn_feat_kernel(const float* __restrict__ feat, const float* __restrict__ qn, in
 #pragma unroll
       for (int l = 0; l < NL; ++l) L[l] = s_L[(r * NL + l) * 32 + lane];
       uint64_t thr = (NL == 2 && K > 32) ? shfl_u64(L[NL - 1], K - 33) : shfl_u64(L[0], K - 1);
+      float thr_f = key_to_float(thr);   // KEY_MAX decodes to NaN: !(d > NaN) lets everything through
       bool dirty = false;
 #pragma unroll
-      for (int c = 0; c < KF_TC / 32; ++c) {
+      for (int c = 0; c < KF2_TC / 32; ++c) {
         const int j = j0 + c * 32 + lane;
+        const float dv = s_D[r * KF2_LDD + c * 32 + lane];
+        // cheap float pre-filter; the exact (distance, index) order is decided on the keys below
+        if (__ballot_sync(0xffffffffu, j < N && !(dv > thr_f)) == 0) continue;
         uint64_t key = KEY_MAX;
-        if (j < N) key = make_key(s_D[r * KF_LDD + c * 32 + lane], (uint32_t)j);
+        if (j < N) key = make_key(dv, (uint32_t)j);
         const bool pass = key < thr;
         unsigned m = __ballot_sync(0xffffffffu, pass);
         if (m == 0) continue;
@@ -168,6 +195,7 @@ knn_feat_kernel(const float* __restrict__ feat, const float* __restrict__ qn, in
           L[0] = warp_bitonic_merge32(lo, lane);
           thr = (NL == 2 && K > 32) ? shfl_u64(L[NL - 1], K - 33) : shfl_u64(L[0], K - 1);
         }
+        thr_f = key_to_float(thr);
       }
       if (dirty) {
 #pragma unroll
@@ -196,7 +224,7 @@ knn_feat_kernel(const float* __restrict__ feat, const float* __restrict__ qn, in
 template <int NL>
 static int launch_knn_feat(const float* feat, const float* qn, int B, int N, int D, int K,
                            int drop, int64_t* idx64, int32_t* idx32, cudaStream_t st) {
-  size_t fl = (size_t)KF_TQ * (D + 4) + KF_TC * KF_LDB + KF_TQ * KF_LDD;
+  size_t fl = (size_t)KF_TQ * (D + 4) + KF_DK * KF2_LDBT + KF_TQ * KF2_LDD;
   fl += fl & 1;  // 8-byte align the lists
   size_t smem = fl * sizeof(float) + (size_t)KF_TQ * NL * 32 * sizeof(uint64_t);
   auto kern = knn_feat_kernel<NL>;
