@@ -291,9 +291,18 @@ def run_b200(args):
     rows = kernel_breakdown(ops.timing_records(), ksteps)
     ops.enable_timing(False)
 
-    if rank != 0:
+    def leave():
+        """NCCL communicators captured in a CUDA graph do not tear down cleanly
+        (destroy_process_group blocks); all ranks meet once more, then exit hard."""
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return
 
     peak, peak_src = peaks()
@@ -326,8 +335,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 if __name__ == "__main__":

@@ -58,6 +58,36 @@ __device__ __forceinline__ uint64_t warp_bitonic_merge32(uint64_t key, int lane)
   return key;
 }
 
+// 32-bit variants (orderable distances only) and the K-th smallest of 64 values held two per lane.
+__device__ __forceinline__ uint32_t warp_sort32_u32(uint32_t key, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, key, j);
+      const bool asc = ((lane & k) == 0), lower = ((lane & j) == 0);
+      key = (asc == lower) ? min(key, other) : max(key, other);
+    }
+  }
+  return key;
+}
+__device__ __forceinline__ uint32_t warp_bitonic_merge32_u32(uint32_t key, int lane) {
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, key, j);
+    key = ((lane & j) == 0) ? min(key, other) : max(key, other);
+  }
+  return key;
+}
+// K-th smallest (1-based K <= 64) of the 64 values {a, b} x 32 lanes.
+__device__ __forceinline__ uint32_t warp_kth_smallest64(uint32_t a, uint32_t b, int K, int lane) {
+  a = warp_sort32_u32(a, lane);
+  b = warp_sort32_u32(b, lane);
+  const uint32_t brev = __shfl_sync(0xffffffffu, b, 31 - lane);
+  if (K <= 32) return __shfl_sync(0xffffffffu, warp_bitonic_merge32_u32(min(a, brev), lane), K - 1);
+  return __shfl_sync(0xffffffffu, warp_bitonic_merge32_u32(max(a, brev), lane), K - 33);
+}
+
 // Running top-K (K <= 32*NL) of a stream of keys, one warp per query.
 // L[0] holds ranks 0..31 (lane = rank), L[1] ranks 32..63 when NL == 2.
 template <int NL>

@@ -87,6 +87,80 @@ __global__ void orl_finish_kernel(const float* __restrict__ partial, int tiles, 
   G[(size_t)b * C + c] = (float)(s / (double)N);
 }
 
+// ORL, shared-memory form: one CTA owns (object, 16-channel slice).  The slice of the feature
+// map (N x 16 fp32, 64 B per point) is staged ONCE into shared memory with coalesced 16-byte
+// loads; every gathered row is then a conflict-free 64-byte shared-memory read by a half-warp
+// (lane = channel, the two halves of a warp work on two points), instead of k dependent L2
+// round trips per point.  The per-object mean is finished inside the CTA in a fixed order
+// (deterministic), so the whole op is one launch and needs no workspace.
+constexpr int ORL_CS = 16;
+constexpr int ORL_THREADS = 256;
+constexpr int ORL_GROUPS = ORL_THREADS / 4;   // point groups per CTA (4 lanes x 4 channels = 16 channels)
+
+template <bool AM>
+__device__ __forceinline__ void orl_take(const float4 v, int n, float4& m, int (&am)[4]) {
+  if (AM) {
+    if (v.x > m.x) { m.x = v.x; am[0] = n; }
+    if (v.y > m.y) { m.y = v.y; am[1] = n; }
+    if (v.z > m.z) { m.z = v.z; am[2] = n; }
+    if (v.w > m.w) { m.w = v.w; am[3] = n; }
+  } else {
+    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+  }
+}
+
+template <bool AM>
+__global__ void __launch_bounds__(ORL_THREADS)
+orl_smem_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx, int N, int C,
+                int k, float* __restrict__ G, uint8_t* __restrict__ argmax) {
+  extern __shared__ __align__(16) float s_f[];            // [N][16]
+  __shared__ float s_sum[ORL_GROUPS][ORL_CS];
+  const int b = blockIdx.y, c0 = blockIdx.x * ORL_CS;
+  const int tid = threadIdx.x;
+  const float* fb = feat + (size_t)b * N * C + c0;
+  for (int e = tid; e < N * (ORL_CS / 4); e += ORL_THREADS) {
+    const int row = e / (ORL_CS / 4), q = e % (ORL_CS / 4);
+    reinterpret_cast<float4*>(s_f)[e] = __ldg(reinterpret_cast<const float4*>(fb + (size_t)row * C) + q);
+  }
+  __syncthreads();
+  // thread = (point group, channel quad): one LDS.128 per gathered row serves 4 channels
+  const int grp = tid >> 2, q = tid & 3;
+  const float4* sf4 = reinterpret_cast<const float4*>(s_f) + q;
+  const int32_t* ib = idx + (size_t)b * N * k;
+  const int k4 = k >> 2;
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = grp; p < N; p += ORL_GROUPS) {
+    const int32_t* ip = ib + (size_t)p * k;
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    int am[4] = {0, 0, 0, 0};
+    if ((k & 3) == 0 && ((size_t)p * k & 3) == 0) {     // 16-byte aligned index row
+      const int4* ip4 = reinterpret_cast<const int4*>(ip);
+      int4 jj = __ldg(ip4);
+      for (int t = 0; t < k4; ++t) {
+        const int4 cur = jj;
+        if (t + 1 < k4) jj = __ldg(ip4 + t + 1);
+        orl_take<AM>(sf4[cur.x * (ORL_CS / 4)], 4 * t, m, am);
+        orl_take<AM>(sf4[cur.y * (ORL_CS / 4)], 4 * t + 1, m, am);
+        orl_take<AM>(sf4[cur.z * (ORL_CS / 4)], 4 * t + 2, m, am);
+        orl_take<AM>(sf4[cur.w * (ORL_CS / 4)], 4 * t + 3, m, am);
+      }
+    } else {
+      for (int n = 0; n < k; ++n) orl_take<AM>(sf4[__ldg(ip + n) * (ORL_CS / 4)], n, m, am);
+    }
+    sum.x += m.x; sum.y += m.y; sum.z += m.z; sum.w += m.w;
+    if (AM)
+      *reinterpret_cast<uchar4*>(argmax + ((size_t)b * N + p) * C + c0 + 4 * q) =
+          make_uchar4((unsigned char)am[0], (unsigned char)am[1], (unsigned char)am[2], (unsigned char)am[3]);
+  }
+  *reinterpret_cast<float4*>(&s_sum[grp][4 * q]) = sum;
+  __syncthreads();
+  if (tid < ORL_CS) {
+    double t = 0.0;
+    for (int g = 0; g < ORL_GROUPS; ++g) t += (double)s_sum[g][tid];
+    G[(size_t)b * C + c0 + tid] = (float)(t / (double)N);
+  }
+}
+
 __global__ void __launch_bounds__(GO_THREADS)
 orl_bwd_kernel(const float* __restrict__ gG, const int32_t* __restrict__ idx,
                const uint8_t* __restrict__ argmax, int N, int C, int k,
@@ -193,6 +267,21 @@ extern "C" int hsp_orl_global_fwd(const float* feat, const int32_t* idx, int B, 
     return HSP_EWORKSPACE;
   const int tile = orl_tile(N), tiles = (N + tile - 1) / tile;
   cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)N * ORL_CS * sizeof(float);
+  if ((C % ORL_CS) == 0 && smem <= 200 * 1024 && (((uintptr_t)argmax) & 3) == 0) {
+    if (smem > 48 * 1024 &&
+        (cudaFuncSetAttribute(orl_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)smem) != cudaSuccess ||
+         cudaFuncSetAttribute(orl_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)smem) != cudaSuccess))
+      return HSP_ELAUNCH;
+    if (argmax)
+      orl_smem_kernel<true><<<dim3(C / ORL_CS, B), ORL_THREADS, smem, st>>>(feat, idx, N, C, k, G, argmax);
+    else
+      orl_smem_kernel<false><<<dim3(C / ORL_CS, B), ORL_THREADS, smem, st>>>(feat, idx, N, C, k, G, nullptr);
+    HSP_LAUNCH_CHECK();
+    return HSP_OK;
+  }
   dim3 grid(tiles, B, (C + GO_THREADS - 1) / GO_THREADS);
   orl_partial_kernel<<<grid, GO_THREADS, 0, st>>>(feat, idx, N, C, k, tile, (float*)workspace,
                                                   argmax);
