@@ -74,6 +74,32 @@ def conv_bn_relu_points(conv: nn.Conv1d, bn: nn.BatchNorm1d, x_bnc, relu=True):
     return bn_points(bn, conv1x1(conv, x_bnc, pad_in), relu=relu)
 
 
+def fused_block_ok(conv: nn.Conv1d, bn: nn.BatchNorm1d, x_bnc):
+    shape = x_bnc.shape
+    return (bn.training and mixed_precision() and x_bnc.is_cuda and conv.out_channels % 8 == 0
+            and shape[-1] % 8 == 0 and x_bnc.numel() // shape[-1] > 1)
+
+
+def multi_conv_bn_relu_points(pairs, x_bnc):
+    """[(conv, bn)] all reading x_bnc -> list of outputs; one autograd node on the mixed path
+    (ops.multi_linear_bn_relu), else the blocks one by one."""
+    shape = x_bnc.shape
+    if not all(fused_block_ok(c, b, x_bnc) for c, b in pairs):
+        return [conv_bn_relu_points(c, b, x_bnc) for c, b in pairs]
+    blocks = []
+    for conv, bn in pairs:
+        w = conv.weight[:, :, 0]
+        pad_in = shape[-1] - conv.in_channels
+        if pad_in:
+            w = F.pad(w, (0, pad_in))
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        blocks.append((w, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
+                       bn.momentum, True))
+    outs = ops.multi_linear_bn_relu(x_bnc.reshape(-1, shape[-1]), blocks)
+    return [z.view(*shape[:-1], c.out_channels) for z, (c, _) in zip(outs, pairs)]
+
+
 def seq_points(seq: nn.Sequential, x_bnc):
     """Run a Conv1d/BatchNorm1d/ReLU nn.Sequential (FaceRecon.py:38-68) in (bs, N, C) layout;
     BN+ReLU pairs are fused; a narrow last conv (3 / 30 channels) is computed 8-aligned."""
@@ -183,11 +209,22 @@ class FaceRecon(nn.Module):
             feat = ops.concat_upsample(pieces, nns, vertice_num)
             self.feat_padded = None
 
+        # heads that read the same feature buffer (PoseNet9D registers them in `joint_first`)
+        # share one autograd node with conv1d_block[0] on the mixed-precision path
+        joint = list(getattr(self, "joint_first", None) or []) if mixed else []
+        self.joint_out = None
         if FLAGS.train:
-            conv1d_out = seq_points(self.conv1d_block, feat_pad if mixed else feat)   # (bs, N, 256)
+            if joint and fused_block_ok(self.conv1d_block[0], self.conv1d_block[1], feat_pad):
+                outs = multi_conv_bn_relu_points(joint + [(self.conv1d_block[0], self.conv1d_block[1])], feat_pad)
+                self.joint_out = outs[:-1]
+                conv1d_out = seq_points(list(self.conv1d_block)[3:], outs[-1])             # (bs, N, 256)
+            else:
+                conv1d_out = seq_points(self.conv1d_block, feat_pad if mixed else feat)   # (bs, N, 256)
             recon = seq_points(self.recon_head, conv1d_out)                            # (bs, N, 3)
             face = self._face_head(f_global, conv1d_out, vertices)                     # (bs, N, 30)
             return recon, face, feat
+        if joint and all(fused_block_ok(c, b, feat_pad) for c, b in joint):
+            self.joint_out = multi_conv_bn_relu_points(joint, feat_pad)
         return None, None, feat
 
     def _face_head(self, f_global, conv1d_out, vertices):

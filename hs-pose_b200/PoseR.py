@@ -27,9 +27,10 @@ class _PointHead(nn.Module):
         self.bn2 = nn.BatchNorm1d(256)
         self.bn3 = nn.BatchNorm1d(256)
 
-    def forward_points(self, x_bnc):
-        # x_bnc may be the 16-aligned padded feature buffer (extra columns get zero weights)
-        x = conv_bn_relu_points(self.conv1, self.bn1, x_bnc)
+    def forward_points(self, x_bnc, first=None):
+        # x_bnc may be the 16-aligned padded feature buffer (extra columns get zero weights);
+        # `first` is relu(bn1(conv1(x))) when PoseNet9D already computed it jointly with the others
+        x = first if first is not None else conv_bn_relu_points(self.conv1, self.bn1, x_bnc)
         x = conv_bn_relu_points(self.conv2, self.bn2, x)
         x = torch.max(x, 1)[0]                                  # (bs, 256): max over points
         x = F.relu(self.bn3(F.linear(x, self.conv3.weight[:, :, 0], self.conv3.bias)))

@@ -12,6 +12,6 @@ class Pose_Ts(_PointHead):
         self.relu2 = nn.ReLU()
         self.relu3 = nn.ReLU()
 
-    def forward_points(self, x_bnc):
-        x = super().forward_points(x_bnc)
+    def forward_points(self, x_bnc, first=None):
+        x = super().forward_points(x_bnc, first)
         return x[:, 0:3], x[:, 3:6]

@@ -392,13 +392,27 @@ surface_conv_bwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict
   }
 }
 
-__global__ void dir_reduce_kernel(const float* __restrict__ partial, int rows, int cols,
-                                  float* __restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= cols) return;
+// Fixed-order column sums of the per-CTA partial rows: block (32 columns, 8 row groups); group g
+// adds rows g, g+8, ... (independent loads), the 8 group sums are then added in order 0..7.
+__global__ void __launch_bounds__(256)
+dir_reduce_kernel(const float* __restrict__ partial, int rows, int cols, float* __restrict__ out,
+                  int cols_a, float* __restrict__ out_b) {
+  __shared__ float sh[8][32];
+  const int j = blockIdx.x * 32 + threadIdx.x;
   float s = 0.0f;
-  for (int r = 0; r < rows; ++r) s += partial[(size_t)r * cols + j];
-  out[j] = s;
+  if (j < cols) {
+#pragma unroll 4
+    for (int r = threadIdx.y; r < rows; r += 8) s += __ldg(partial + (size_t)r * cols + j);
+  }
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < cols) {
+    float t = 0.0f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += sh[g][threadIdx.x];
+    if (j < cols_a) out[j] = t;
+    else if (out_b) out_b[j - cols_a] = t;
+  }
 }
 
 template <int S, typename TP>
@@ -406,16 +420,17 @@ __global__ void __launch_bounds__(GC_THREADS)
 graph_conv_bwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
                       const float* __restrict__ dirn, const TP* __restrict__ P,
                       const uint8_t* __restrict__ argmax, const float* __restrict__ gout, int B,
-                      int N, int k, int C, float* __restrict__ gP, float* __restrict__ partial) {
+                      int N, int k, int C, float* __restrict__ gP, float* __restrict__ partial,
+                      int want_gbias) {
   __shared__ int s_idx[GC_PT * GC_MAXK];
   __shared__ float s_r[GC_PT * GC_MAXK * 3];
   const int c = blockIdx.z * GC_THREADS + threadIdx.x;
   const int SC = S * C, LD = (S + 1) * C;
   const int tiles = (N + GC_PT - 1) / GC_PT;
-  float dx[S], dy[S], dz[S], gx[S], gy[S], gz[S];
+  float dx[S], dy[S], dz[S], gx[S], gy[S], gz[S], gb[S], gbc = 0.0f;   // gb*: column sums of gP
 #pragma unroll
   for (int s = 0; s < S; ++s) {
-    gx[s] = gy[s] = gz[s] = 0.0f;
+    gx[s] = gy[s] = gz[s] = gb[s] = 0.0f;
     dx[s] = dy[s] = dz[s] = 0.0f;
     if (c < C) {
       dx[s] = dirn[s * C + c];
@@ -436,6 +451,7 @@ graph_conv_bwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__
         const size_t row = (size_t)b * N + i0 + p;
         const float g = gout[row * C + c];
         gPb[(size_t)(i0 + p) * LD + c] = g;  // centre term
+        gbc += g;
         const float gs = __fdiv_rn(g, (float)S);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -445,6 +461,7 @@ graph_conv_bwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__
           const float th = fmaxf(fmaf(r[2], dz[s], fmaf(r[1], dy[s], r[0] * dx[s])), 0.0f);
           if (th > 0.0f) {
             atomicAdd(gPb + off, gs * th);
+            gb[s] += gs * th;
             const float gv = gs * ld_p(Pb + off);
             gx[s] = fmaf(gv, r[0], gx[s]);
             gy[s] = fmaf(gv, r[1], gy[s]);
@@ -455,12 +472,18 @@ graph_conv_bwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__
     }
   }
   if (c < C) {
-    float* pr = partial + (size_t)blockIdx.x * 3 * SC;
+    const int pcols = want_gbias ? 3 * SC + (S + 1) * C : 3 * SC;
+    float* pr = partial + (size_t)blockIdx.x * pcols;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       pr[s * C + c] = gx[s];
       pr[SC + s * C + c] = gy[s];
       pr[2 * SC + s * C + c] = gz[s];
+    }
+    if (want_gbias) {       // bias layout of HS_layer: [centre C | s*C + c]
+      pr[3 * SC + c] = gbc;
+#pragma unroll
+      for (int s = 0; s < S; ++s) pr[3 * SC + C + s * C + c] = gb[s];
     }
   }
 }
@@ -541,7 +564,9 @@ extern "C" size_t hsp_surface_conv_bwd_workspace_bytes(int B, int N, int k, int 
   return (size_t)bwd_ctas(B, N) * 3 * S * C * sizeof(float);
 }
 extern "C" size_t hsp_graph_conv_bwd_workspace_bytes(int B, int N, int k, int S, int C) {
-  return hsp_surface_conv_bwd_workspace_bytes(B, N, k, S, C);
+  using namespace hsp;
+  if (bad_dims(B, N, k, S, C) || B == 0) return 0;
+  return (size_t)bwd_ctas(B, N) * (3 * S + S + 1) * C * sizeof(float);
 }
 
 extern "C" int hsp_surface_conv_bwd(const float* xyz, const int32_t* idx, const uint8_t* argmax,
@@ -563,7 +588,8 @@ extern "C" int hsp_surface_conv_bwd(const float* xyz, const int32_t* idx, const 
                         xyz, idx, argmax, gout, B, N, k, C, (float*)workspace)));
   HSP_LAUNCH_CHECK();
   const int cols = 3 * S * C;
-  dir_reduce_kernel<<<(cols + 127) / 128, 128, 0, st>>>((const float*)workspace, ctas, cols, gdirn);
+  dir_reduce_kernel<<<(cols + 31) / 32, dim3(32, 8), 0, st>>>((const float*)workspace, ctas, cols, gdirn,
+                                                          cols, nullptr);
   HSP_LAUNCH_CHECK();
   return HSP_OK;
 }
@@ -571,19 +597,22 @@ extern "C" int hsp_surface_conv_bwd(const float* xyz, const int32_t* idx, const 
 extern "C" int hsp_graph_conv_bwd(const float* xyz, const int32_t* idx, const float* dirn,
                                   const void* P, int p_dtype, const uint8_t* argmax,
                                   const float* gout, int B, int N, int k, int S, int C, float* gP,
-                                  float* gdirn, void* workspace, size_t workspace_bytes,
-                                  void* stream) {
+                                  float* gdirn, float* gbias, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
   using namespace hsp;
   if (!xyz || !idx || !dirn || !P || !argmax || !gout || !gP || !gdirn ||
       bad_dims(B, N, k, S, C))
     return HSP_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   if (B == 0) {
+    if (gbias && cudaMemsetAsync(gbias, 0, sizeof(float) * (S + 1) * C, st) != cudaSuccess)
+      return HSP_ELAUNCH;
     return cudaMemsetAsync(gdirn, 0, sizeof(float) * 3 * S * C, st) == cudaSuccess ? HSP_OK
                                                                                    : HSP_ELAUNCH;
   }
   if (!workspace || workspace_bytes < hsp_graph_conv_bwd_workspace_bytes(B, N, k, S, C))
     return HSP_EWORKSPACE;
+  const int want_gbias = gbias != nullptr;
   if (cudaMemsetAsync(gP, 0, sizeof(float) * (size_t)B * N * (S + 1) * C, st) != cudaSuccess)
     return HSP_ELAUNCH;
   const int ctas = bwd_ctas(B, N);
@@ -591,17 +620,18 @@ extern "C" int hsp_graph_conv_bwd(const float* xyz, const int32_t* idx, const fl
   if (p_dtype == HSP_DTYPE_BF16) {
     HSP_DISPATCH_S(S, (graph_conv_bwd_kernel<S, __nv_bfloat16><<<grid, GC_THREADS, 0, st>>>(
                           xyz, idx, dirn, (const __nv_bfloat16*)P, argmax, gout, B, N, k, C, gP,
-                          (float*)workspace)));
+                          (float*)workspace, want_gbias)));
   } else if (p_dtype == HSP_DTYPE_F32) {
     HSP_DISPATCH_S(S, (graph_conv_bwd_kernel<S, float><<<grid, GC_THREADS, 0, st>>>(
                           xyz, idx, dirn, (const float*)P, argmax, gout, B, N, k, C, gP,
-                          (float*)workspace)));
+                          (float*)workspace, want_gbias)));
   } else {
     return HSP_EINVAL;
   }
   HSP_LAUNCH_CHECK();
-  const int cols = 3 * S * C;
-  dir_reduce_kernel<<<(cols + 127) / 128, 128, 0, st>>>((const float*)workspace, ctas, cols, gdirn);
+  const int cols_a = 3 * S * C, cols = want_gbias ? cols_a + (S + 1) * C : cols_a;
+  dir_reduce_kernel<<<(cols + 31) / 32, dim3(32, 8), 0, st>>>((const float*)workspace, ctas, cols, gdirn,
+                                                          cols_a, gbias);
   HSP_LAUNCH_CHECK();
   return HSP_OK;
 }

@@ -174,7 +174,7 @@ def _graph_conv_fwd_raw(xyz, idx32, dirn, P, S, C, want_argmax):
     return out, am
 
 
-def _graph_conv_bwd_raw(xyz, idx32, dirn, P, am, gout, S, C):
+def _graph_conv_bwd_raw(xyz, idx32, dirn, P, am, gout, S, C, want_gbias=False):
     B, N, k = idx32.shape
     dt = BF16 if P.dtype == torch.bfloat16 else F32
     with torch.cuda.device(xyz.device):
@@ -182,9 +182,10 @@ def _graph_conv_bwd_raw(xyz, idx32, dirn, P, am, gout, S, C):
         ws = _workspace(lib.hsp_graph_conv_bwd_workspace_bytes(B, N, k, S, C), xyz.device)
         gP = torch.empty(B, N, (S + 1) * C, dtype=torch.float32, device=xyz.device)
         gdirn = torch.empty_like(dirn)
+        gbias = torch.empty((S + 1) * C, dtype=torch.float32, device=xyz.device) if want_gbias else None
         _call("hsp_graph_conv_bwd", _p(xyz), _p(idx32), _p(dirn), _p(P), dt, _p(am), _p(gout),
-              B, N, k, S, C, _p(gP), _p(gdirn), _p(ws), ws.numel(), _stream())
-    return gP, gdirn
+              B, N, k, S, C, _p(gP), _p(gdirn), _p(gbias), _p(ws), ws.numel(), _stream())
+    return (gP, gdirn, gbias) if want_gbias else (gP, gdirn)
 
 
 class _GraphConv(torch.autograd.Function):
@@ -247,7 +248,7 @@ class _HSConvMixed(torch.autograd.Function):
         S, C = ctx.dims
         B, N, Cin = fm.shape
         gout = _need(gout.float(), torch.float32, "gout")
-        gP, gdirn = _graph_conv_bwd_raw(xyz, idx32, dirn, P, am, gout, S, C)
+        gP, gdirn, gb = _graph_conv_bwd_raw(xyz, idx32, dirn, P, am, gout, S, C, want_gbias=True)
         gP2 = gP.view(B * N, (S + 1) * C)
         with torch.autocast("cuda", enabled=False):
             prev = torch.backends.cuda.matmul.allow_tf32
@@ -257,7 +258,6 @@ class _HSConvMixed(torch.autograd.Function):
                 gW = fm.reshape(B * N, Cin).t() @ gP2
             finally:
                 torch.backends.cuda.matmul.allow_tf32 = prev
-            gb = gP2.sum(dim=0)
         return None, None, gdirn, gfm, gW, gb, None, None
 
 
@@ -549,6 +549,64 @@ class _LinearBnRelu(torch.autograd.Function):
 def linear_bn_relu(x, W, b, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, relu=True):
     """Fused Linear -> BatchNorm(train) -> ReLU on a (M,K) matrix (bf16 compute)."""
     return _LinearBnRelu.apply(x, W, b, gamma, beta, running_mean, running_var, eps, momentum, relu)
+
+
+class _MultiLinearBnRelu(torch.autograd.Function):
+    """Several Conv1d(k=1) -> BatchNorm1d -> ReLU blocks that read the SAME (M,K) input (the
+    1286-channel feature buffer feeds rot_green.conv1, rot_red.conv1, ts.conv1 and
+    conv1d_block[0]: reference PoseNet9D.py:37-50, FaceRecon.py:114-116) as one autograd node.
+    The input gradient is accumulated inside the dgrad GEMMs (beta = 1) instead of by separate
+    full-size add passes."""
+
+    @staticmethod
+    def forward(ctx, x, buffers, *params):
+        # params: (W, b, gamma, beta) per block; buffers: [(running_mean, running_var, eps, momentum, relu)]
+        xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+        n = len(buffers)
+        saved, outs, meta = [xb], [], []
+        for i in range(n):
+            W, b, gamma, beta = params[4 * i:4 * i + 4]
+            rm, rv, eps, mom, relu = buffers[i]
+            Wb = W.to(torch.bfloat16)
+            with torch.autocast("cuda", enabled=False):
+                y = torch.addmm(b.to(torch.bfloat16), xb, Wb.t()) if b is not None else xb @ Wb.t()
+            g32, b32 = gamma.float().contiguous(), beta.float().contiguous()
+            z, stats = _bn_fwd_raw(y, g32, b32, rm, rv, eps, mom, relu)
+            saved += [Wb, y, g32, b32, stats]
+            meta.append((int(relu), b is not None))
+            outs.append(z)
+        ctx.save_for_backward(*saved)
+        ctx.meta = meta
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *dzs):
+        saved = ctx.saved_tensors
+        xb = saved[0]
+        grads, dx = [], None
+        for i, (relu, has_bias) in enumerate(ctx.meta):
+            Wb, y, g32, b32, stats = saved[1 + 5 * i:6 + 5 * i]
+            dz = dzs[i]
+            if dz is None:
+                grads += [None, None, None, None]
+                continue
+            dy, dgamma, dbeta, colsum = _bn_bwd_raw(y, dz, g32, b32, stats, relu, has_bias)
+            with torch.autocast("cuda", enabled=False):
+                if ctx.needs_input_grad[0]:
+                    dx = dy @ Wb if dx is None else dx.addmm_(dy, Wb)
+                dW = (dy.t() @ xb).float()
+            grads += [dW, colsum, dgamma, dbeta]
+        return (dx, None, *grads)
+
+
+def multi_linear_bn_relu(x, blocks):
+    """blocks: list of (W, b, gamma, beta, running_mean, running_var, eps, momentum, relu).
+    Returns the list of relu?(bn_train(x @ W_i^T + b_i))."""
+    params, buffers = [], []
+    for W, b, gamma, beta, rm, rv, eps, mom, relu in blocks:
+        params += [W, b, gamma, beta]
+        buffers.append((rm, rv, eps, mom, relu))
+    return list(_MultiLinearBnRelu.apply(x, buffers, *params))
 
 
 # ---------------------------------------------------------------- chamfer

@@ -112,12 +112,15 @@ int hsp_graph_conv_fwd(const float* xyz, const int32_t* idx, const float* dirn,
                        const void* P, int p_dtype, int B, int N, int k, int S, int C,
                        float* out, uint8_t* argmax, void* stream);
 /* Backward: gP (B,N,(S+1)*C) (overwritten: centre part = gout, support part
- * = scatter of gout/S*theta to the winning neighbour rows), gdirn (3,S*C).  */
+ * = scatter of gout/S*theta to the winning neighbour rows), gdirn (3,S*C), and
+ * optionally gbias ((S+1)*C, may be NULL) = column sums of gP — the gradient of
+ * HS_layer.bias (gcn3d.py:170) — accumulated in registers alongside gdirn, so no
+ * separate reduction pass over gP is needed.                                 */
 size_t hsp_graph_conv_bwd_workspace_bytes(int B, int N, int k, int S, int C);
 int hsp_graph_conv_bwd(const float* xyz, const int32_t* idx, const float* dirn,
                        const void* P, int p_dtype, const uint8_t* argmax, const float* gout,
                        int B, int N, int k, int S, int C, float* gP, float* gdirn,
-                       void* workspace, size_t workspace_bytes, void* stream);
+                       float* gbias, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ K5 ---
  * Row gather + max over neighbours, evaluated at selected rows only:
