@@ -210,8 +210,10 @@ template <> struct Pair<__nv_bfloat16> {
 // the candidate, one LOP3 + one FMNMX; value error <= 2^-17 relative — used with bf16 P, whose
 // own rounding is 2^-9).  CT: compile-time channel count (0 = runtime C) so that the S support
 // loads of a neighbour row are immediate offsets from one base address.
-template <int S, typename TP, int AM, int CT>
-__global__ void __launch_bounds__(GC2_THREADS)
+// UNR / MINB: measured on B200 (tools/kvar.py): 4 neighbours in flight per thread at 4 CTAs/SM
+// (126 registers) beats both deeper unrolling and higher occupancy — the gather is latency-bound.
+template <int S, typename TP, int AM, int CT, int UNR = 4, int MINB = 4>
+__global__ void __launch_bounds__(GC2_THREADS, MINB)
 graph_conv_fwd2_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
                        const float* __restrict__ dirn, const TP* __restrict__ P, int N, int k,
                        int Crt, int lanes_c, float* __restrict__ out, uint8_t* __restrict__ argmax) {
@@ -253,7 +255,7 @@ graph_conv_fwd2_kernel(const float* __restrict__ xyz, const int32_t* __restrict_
     int am0[S], am1[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) { acc[s] = make_float2(-INFINITY, -INFINITY); am0[s] = 0; am1[s] = 0; }
-#pragma unroll 2
+#pragma unroll UNR
     for (int n = 0; n < k; ++n) {
       const float4 rn = s_rn[p * k + n];
       const TP* sup = Pb + (size_t)__float_as_int(rn.w) * LD;
