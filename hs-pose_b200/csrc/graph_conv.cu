@@ -306,6 +306,77 @@ graph_conv_fwd2_kernel(const float* __restrict__ xyz, const int32_t* __restrict_
   }
 }
 
+// K3 forward, v2: channel pairs on the packed-FP32 datapath (see graph_conv_fwd2_kernel).
+// theta for two channels = FMUL2 + 2 FFMA2; max/argmax per element on the ALU pipe.
+template <int S, bool AM>
+__global__ void __launch_bounds__(GC2_THREADS, 4)
+surface_conv_fwd2_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
+                         const float* __restrict__ dirn, int N, int k, int C, int lanes_c,
+                         float* __restrict__ out, uint8_t* __restrict__ argmax) {
+  __shared__ float4 s_rn[GC_PT * GC_MAXK];
+  const int b = blockIdx.y, i0 = blockIdx.x * GC_PT;
+  const int npts = min(GC_PT, N - i0);
+  const int SC = S * C;
+  const float* xb = xyz + (size_t)b * N * 3;
+  const int32_t* ib = idx + (size_t)b * N * k;
+  for (int p = threadIdx.x; p < npts * k; p += GC2_THREADS) {
+    const int i = i0 + p / k;
+    const int nb = ib[(size_t)i * k + (p % k)];
+    float r[3];
+    unit_dir(xb, i, nb, r);
+    s_rn[p] = make_float4(r[0], r[1], r[2], 0.0f);
+  }
+  const int pts_par = GC2_THREADS / lanes_c;
+  const int lane_c = threadIdx.x % lanes_c, psub = threadIdx.x / lanes_c;
+  const int c = (blockIdx.z * lanes_c + lane_c) * 2;
+  const bool active = psub < pts_par && c < C;
+  float2 dx[S], dy[S], dz[S];
+  if (active) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      dx[s] = *reinterpret_cast<const float2*>(dirn + s * C + c);
+      dy[s] = *reinterpret_cast<const float2*>(dirn + SC + s * C + c);
+      dz[s] = *reinterpret_cast<const float2*>(dirn + 2 * SC + s * C + c);
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  for (int p = psub; p < npts; p += pts_par) {
+    float2 acc[S];
+    int am0[S], am1[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { acc[s] = make_float2(0.0f, 0.0f); am0[s] = 255; am1[s] = 255; }
+#pragma unroll 4
+    for (int n = 0; n < k; ++n) {
+      const float4 rn = s_rn[p * k + n];
+      const float2 rx = make_float2(rn.x, rn.x), ry = make_float2(rn.y, rn.y), rz = make_float2(rn.z, rn.z);
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const float2 t = __ffma2_rn(rz, dz[s], __ffma2_rn(ry, dy[s], __fmul2_rn(rx, dx[s])));
+        if (AM) {
+          if (t.x > acc[s].x) { acc[s].x = t.x; am0[s] = n; }
+          if (t.y > acc[s].y) { acc[s].y = t.y; am1[s] = n; }
+        } else {
+          acc[s].x = fmaxf(acc[s].x, t.x);
+          acc[s].y = fmaxf(acc[s].y, t.y);
+        }
+      }
+    }
+    float sx = 0.0f, sy = 0.0f;
+#pragma unroll
+    for (int s = 0; s < S; ++s) { sx += acc[s].x; sy += acc[s].y; }
+    const size_t row = (size_t)b * N + i0 + p;
+    *reinterpret_cast<float2*>(out + row * C + c) =
+        make_float2(__fdiv_rn(sx, (float)S), __fdiv_rn(sy, (float)S));
+    if (AM) {
+#pragma unroll
+      for (int s = 0; s < S; ++s)
+        *reinterpret_cast<uchar2*>(argmax + row * SC + s * C + c) =
+            make_uchar2((unsigned char)am0[s], (unsigned char)am1[s]);
+    }
+  }
+}
+
 template <int S, typename TP, int AM>
 static void launch_gc2(dim3 grid2, cudaStream_t st, const float* xyz, const int32_t* idx,
                        const float* dirn, const TP* P, int N, int k, int C, int lanes_c, float* out,
@@ -522,6 +593,17 @@ extern "C" int hsp_surface_conv_fwd(const float* xyz, const int32_t* idx, const 
   if (B == 0) return HSP_OK;
   dim3 grid((N + GC_PT - 1) / GC_PT, B, (C + GC_THREADS - 1) / GC_THREADS);
   cudaStream_t st = (cudaStream_t)stream;
+  if ((C & 1) == 0 && S == 7 && (((uintptr_t)argmax) & 1) == 0) {   // v2: channel pairs, packed FP32
+    const int pairs = C / 2;
+    const int lanes_c = pairs < GC2_THREADS ? pairs : GC2_THREADS;
+    dim3 grid2((N + GC_PT - 1) / GC_PT, B, (pairs + lanes_c - 1) / lanes_c);
+    if (argmax)
+      surface_conv_fwd2_kernel<7, true><<<grid2, GC2_THREADS, 0, st>>>(xyz, idx, dirn, N, k, C, lanes_c, out, argmax);
+    else
+      surface_conv_fwd2_kernel<7, false><<<grid2, GC2_THREADS, 0, st>>>(xyz, idx, dirn, N, k, C, lanes_c, out, nullptr);
+    HSP_LAUNCH_CHECK();
+    return HSP_OK;
+  }
   HSP_DISPATCH_S(S, (surface_conv_fwd_kernel<S><<<grid, GC_THREADS, 0, st>>>(xyz, idx, dirn, N, k, C, out, argmax)));
   HSP_LAUNCH_CHECK();
   return HSP_OK;

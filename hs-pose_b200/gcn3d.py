@@ -144,13 +144,20 @@ def get_ORL_global(feature, vertices, neighbor_num):
     return G.unsqueeze(1).repeat(1, feature.size(1), 1)
 
 
-def _orl_fuse(feature, vertices, neighbor_num, conv2_weight):
+def _orl_fuse(feature, vertices, neighbor_num, conv2_weight, f_STE=None):
     """ORL_forward (gcn3d.py:109-113 / :183-187) without the cat/repeat:
-    conv2(cat[f, G]) = f @ W2[:, :C]^T + (G @ W2[:, C:]^T) broadcast over points."""
+    conv2(cat[f, G]) = f @ W2[:, :C]^T + (G @ W2[:, C:]^T) broadcast over points, and the
+    layer's `+ f_STE` (gcn3d.py:90 / :156) folded into the same pass (K5d) when given."""
     C = feature.shape[2]
     G = ops.orl_global(feature, _geo_index32_exact(vertices, neighbor_num))  # (B,C)
     W2 = conv2_weight[:, :, 0]
-    return feature + F.linear(feature, W2[:, :C]) + F.linear(G, W2[:, C:]).unsqueeze(1)
+    lin = F.linear(feature, W2[:, :C])
+    with torch.autocast("cuda", enabled=False):
+        gproj = F.linear(G.float(), W2[:, C:].float())                       # (B,C), tiny: keep fp32
+    if C % 4 == 0 and feature.dtype == torch.float32:
+        return ops.residual_sum(feature, lin, gproj, f_STE)
+    out = feature + lin + gproj.unsqueeze(1)
+    return out if f_STE is None else out + f_STE
 
 
 # -------------------------------------------------------------------- layers
@@ -177,8 +184,7 @@ class HSlayer_surface(nn.Module):
         with torch.autocast("cuda", enabled=False):   # K = 3: keep the coordinates in fp32
             f_STE = F.linear(vertices.float(), self.STE_layer.weight[:, :, 0])
         feature = self.graph_conv(None, vertices, neighbor_num)
-        feature = self.ORL_forward(feature, vertices, neighbor_num)
-        return feature + f_STE
+        return _orl_fuse(feature, vertices, neighbor_num, self.conv2.weight, f_STE)
 
     def graph_conv(self, receptive_fields_norm, vertices, neighbor_num):
         """K3.  `receptive_fields_norm` is accepted for signature parity and ignored:
@@ -219,8 +225,7 @@ class HS_layer(nn.Module):
         f_STE = F.linear(feature_map, self.STE_layer.weight[:, :, 0])
         neighbor_index = _feature_index32(feature_map, neighbor_num)          # RF-F (K2)
         feature = self.graph_conv(None, neighbor_index, feature_map, vertices, neighbor_num)
-        feature_fuse = self.ORL_forward(feature, vertices, neighbor_num)
-        return feature_fuse + f_STE
+        return _orl_fuse(feature, vertices, neighbor_num, self.conv2.weight, f_STE)
 
     def graph_conv(self, receptive_fields_norm, neighbor_index, feature_map, vertices,
                    neighbor_num):

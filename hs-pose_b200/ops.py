@@ -451,6 +451,57 @@ def concat_upsample(pieces, nns, M, ld=None, out_dtype=torch.float32):
     return _ConcatUpsample.apply(M, list(nns), ld, out_dtype, *pieces)
 
 
+class _ResidualSum(torch.autograd.Function):
+    """out = feature + lin + gproj[:, None, :] + ste in one pass (K5d); backward = one pass that
+    emits the bf16 cast of the gradient (for bf16 lin / ste) and the per-object column sums."""
+
+    @staticmethod
+    def forward(ctx, feature, lin, gproj, ste):
+        feature = _need(feature, torch.float32, "feature")
+        B, N, C = feature.shape
+
+        def prep(t, name):
+            if t is None:
+                return None, F32
+            if t.dtype not in (torch.float32, torch.bfloat16) or t.shape != feature.shape:
+                raise TypeError(f"{name}: expected (B,N,C) fp32/bf16")
+            return (t if t.is_contiguous() else t.contiguous()), (BF16 if t.dtype == torch.bfloat16 else F32)
+        lin, ldt = prep(lin, "lin")
+        ste, sdt = prep(ste, "ste")
+        gproj = _need(gproj, torch.float32, "gproj") if gproj is not None else None
+        with torch.cuda.device(feature.device):
+            out = torch.empty_like(feature)
+            _call("hsp_residual_sum_fwd", _p(feature), _p(lin), ldt, _p(gproj), _p(ste), sdt, B, N, C,
+                  _p(out), _stream())
+        ctx.meta = (B, N, C, None if lin is None else ldt, None if ste is None else sdt, gproj is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, N, C, ldt, sdt, has_gp = ctx.meta
+        g = _need(g.float(), torch.float32, "g")
+        want16 = (ldt == BF16 and ctx.needs_input_grad[1]) or (sdt == BF16 and ctx.needs_input_grad[3])
+        want_gp = has_gp and ctx.needs_input_grad[2]
+        g16 = ggp = None
+        if want16 or want_gp:
+            with torch.cuda.device(g.device):
+                g16 = torch.empty(B, N, C, dtype=torch.bfloat16, device=g.device) if want16 else None
+                ggp = torch.empty(B, C, dtype=torch.float32, device=g.device) if want_gp else None
+                _call("hsp_residual_sum_bwd", _p(g), B, N, C, _p(g16), _p(ggp), _stream())
+
+        def pick(dt, need):
+            if dt is None or not need:
+                return None
+            return g16 if dt == BF16 else g
+        return (g if ctx.needs_input_grad[0] else None, pick(ldt, ctx.needs_input_grad[1]), ggp,
+                pick(sdt, ctx.needs_input_grad[3]))
+
+
+def residual_sum(feature, lin=None, gproj=None, ste=None):
+    """K5d: feature + lin + gproj[:, None, :] + ste  ((B,N,C); gproj (B,C))."""
+    return _ResidualSum.apply(feature, lin, gproj, ste)
+
+
 # ------------------------------------------------------------ BatchNorm + ReLU
 class _BnRelu(torch.autograd.Function):
     """Batch-statistics BatchNorm1d (+ReLU) on a (M,C) matrix (K6b); x may be a column

@@ -166,6 +166,22 @@ int hsp_upsample_rows_bwd(const void* gout, const int32_t* nn, int B, int Nsrc,
                           int M, int C, int ldo, int col0, int gout_dtype, float* gfeat,
                           void* stream);
 
+/* ----------------------------------------------------------------- K5d ---
+ * The residual sum that closes every HS layer (gcn3d.py:109-113 / :183-187 and
+ * the `+ f_STE` of :90 / :156), one pass:
+ *   out[b,i,c] = feature[b,i,c] + lin[b,i,c] + gproj[b,c] + ste[b,i,c]
+ * lin = feature @ W2[:, :C]^T and ste = STE(layer input) are (B,N,C) fp32 or bf16
+ * (HSP_DTYPE_*), gproj = G @ W2[:, C:]^T is (B,C) fp32; lin, gproj, ste may each
+ * be NULL.  C % 4 == 0.
+ * bwd: g = d out (B,N,C) fp32.  g_bf16 (B,N,C) bf16 (optional) = cast(g) — the
+ * gradient of a bf16 lin / ste; g_gproj (B,C) (optional) = sum_i g[b,i,:].
+ * d feature = g needs no kernel.                                            */
+int hsp_residual_sum_fwd(const float* feature, const void* lin, int lin_dtype,
+                         const float* gproj, const void* ste, int ste_dtype, int B, int N,
+                         int C, float* out, void* stream);
+int hsp_residual_sum_bwd(const float* g, int B, int N, int C, void* g_bf16, float* g_gproj,
+                         void* stream);
+
 /* ------------------------------------------------------------------ K7 ---
  * Chamfer distance (tools/pyTorchChamferDistance/chamfer_distance.cu:6-187):
  * for each point of a (B,N,3) the squared distance to / index of the nearest

@@ -409,3 +409,26 @@ def test_linear_bn_relu_fused_vs_torch(cuda):
     _, stats = o._bn_fwd_raw(yb, gamma, beta, None, None, 1e-5, 0.1, True)
     dy, _, _, cs = o._bn_bwd_raw(yb, dz.to(torch.bfloat16), gamma, beta, stats, 1, True)
     assert torch.allclose(cs, dy.float().sum(0), atol=2e-2, rtol=1e-3)
+
+
+@pytest.mark.parametrize("ldt,sdt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                     (torch.bfloat16, torch.float32)])
+def test_residual_sum_fwd_bwd_vs_torch(cuda, ldt, sdt):
+    """K5d: feature + lin + gproj[:, None] + ste in one pass; gradients = g, cast(g), column sums."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    B, N, C = 3, 257, 256
+    feat = torch.randn(B, N, C, generator=g).to(cuda).requires_grad_()
+    lin = torch.randn(B, N, C, generator=g).to(cuda).to(ldt).requires_grad_()
+    gp = torch.randn(B, C, generator=g).to(cuda).requires_grad_()
+    ste = torch.randn(B, N, C, generator=g).to(cuda).to(sdt).requires_grad_()
+    go = torch.randn(B, N, C, generator=g).to(cuda)
+    out = ops.residual_sum(feat, lin, gp, ste)
+    out.backward(go)
+    ref = feat.detach() + lin.detach().float() + gp.detach()[:, None, :] + ste.detach().float()
+    assert torch.allclose(out, ref, atol=1e-6)
+    assert torch.equal(feat.grad, go)
+    assert torch.allclose(gp.grad, go.sum(1), atol=1e-4)
+    assert torch.equal(lin.grad, go.to(ldt)) and torch.equal(ste.grad, go.to(sdt))
+    out2 = ops.residual_sum(feat.detach(), None, None, ste.detach())     # optional terms
+    assert torch.allclose(out2, feat.detach() + ste.detach().float(), atol=1e-6)
