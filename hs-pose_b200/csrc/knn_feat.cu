@@ -67,6 +67,7 @@ __device__ __forceinline__ float key_to_float(uint64_t key) {
 constexpr int KF2_TC = 128;                 // candidates per tile (16 tx x 4 pairs x 2)
 constexpr int KF2_LDBT = KF2_TC + 2;        // transposed chunk pitch (8-byte aligned rows)
 constexpr int KF2_LDD = KF2_TC + 1;
+constexpr int KF2_PF = KF2_TC * (KF_DK / 4) / KF_THREADS;   // float4 per thread per chunk
 
 template <int NL>
 __global__ void __launch_bounds__(KF_THREADS, 2)
@@ -99,6 +100,14 @@ knn_feat_kernel(const float* __restrict__ feat, const float* __restrict__ qn, in
     qi[r] = i < N ? __ldg(qb + i) : 0.0f;
   }
 
+  float4 pf[KF2_PF];   // register prefetch of the next transposed chunk (128 rows x 32 features)
+#pragma unroll
+  for (int u = 0; u < KF2_PF; ++u) {
+    const int e = tid + u * KF_THREADS;
+    const int r = e / (KF_DK / 4), d4 = e % (KF_DK / 4);
+    pf[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < N) pf[u] = __ldg(reinterpret_cast<const float4*>(fb + (size_t)r * D) + d4);
+  }
   for (int j0 = 0; j0 < N; j0 += KF2_TC) {
     float2 acc[KF_MQ][4];
 #pragma unroll
@@ -108,16 +117,27 @@ knn_feat_kernel(const float* __restrict__ feat, const float* __restrict__ qn, in
 
     for (int d0 = 0; d0 < D; d0 += KF_DK) {
       __syncthreads();  // previous chunk / previous tile's selection done with s_BT / s_D
-      // stage the chunk transposed: lanes walk d fastest (coalesced 128-byte row pieces)
-      for (int e = tid; e < KF2_TC * (KF_DK / 4); e += KF_THREADS) {
+      // stage the chunk transposed from the registers prefetched during the previous chunk
+#pragma unroll
+      for (int u = 0; u < KF2_PF; ++u) {
+        const int e = tid + u * KF_THREADS;
         const int r = e / (KF_DK / 4), d4 = e % (KF_DK / 4);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j0 + r < N)
-          v = __ldg(reinterpret_cast<const float4*>(fb + (size_t)(j0 + r) * D + d0) + d4);
         float* dst = s_BT + (4 * d4) * KF2_LDBT + r;
-        dst[0] = v.x; dst[KF2_LDBT] = v.y; dst[2 * KF2_LDBT] = v.z; dst[3 * KF2_LDBT] = v.w;
+        dst[0] = pf[u].x; dst[KF2_LDBT] = pf[u].y; dst[2 * KF2_LDBT] = pf[u].z; dst[3 * KF2_LDBT] = pf[u].w;
       }
       __syncthreads();
+      {   // prefetch the next chunk (next d0, or chunk 0 of the next tile): in flight during the FMAs
+        int nj0 = j0, nd0 = d0 + KF_DK;
+        if (nd0 >= D) { nd0 = 0; nj0 = j0 + KF2_TC; }
+#pragma unroll
+        for (int u = 0; u < KF2_PF; ++u) {
+          const int e = tid + u * KF_THREADS;
+          const int r = e / (KF_DK / 4), d4 = e % (KF_DK / 4);
+          pf[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (nj0 + r < N)
+            pf[u] = __ldg(reinterpret_cast<const float4*>(fb + (size_t)(nj0 + r) * D + nd0) + d4);
+        }
+      }
 #pragma unroll
       for (int d4 = 0; d4 < KF_DK / 4; ++d4) {
         float4 a[KF_MQ];
