@@ -16,6 +16,8 @@
 // warp updates the sorted top-K lists of its rows: chunks with no candidate
 // under the row's K-th distance cost one ballot; a few candidates are inserted
 // by warp-cooperative shifting; many are bitonic-sorted and merged.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hsp {
@@ -261,9 +263,17 @@ static int launch_knn_feat(const float* feat, const float* qn, int B, int N, int
 
 }  // namespace hsp
 
+namespace hsp {
+size_t knn_feat_tc_workspace_bytes(int B, int N);
+int knn_feat_tc_launch(const float* feat, int B, int N, int K, int drop, int64_t* idx64, int32_t* idx32,
+                       void* workspace, cudaStream_t st);
+}  // namespace hsp
+
 extern "C" size_t hsp_knn_feat_workspace_bytes(int B, int N) {
   if (B <= 0 || N <= 0) return 0;
-  return (size_t)B * N * sizeof(float);
+  const size_t exact = (size_t)B * N * sizeof(float);
+  const size_t tcw = hsp::knn_feat_tc_workspace_bytes(B, N);   // D = 128 tensor-core filter path
+  return exact > tcw ? exact : tcw;
 }
 
 extern "C" int hsp_knn_feat(const float* feat, int B, int N, int D, int k, int drop_first,
@@ -278,6 +288,11 @@ extern "C" int hsp_knn_feat(const float* feat, int B, int N, int D, int k, int d
   if (B == 0) return HSP_OK;
   if (!workspace || workspace_bytes < hsp_knn_feat_workspace_bytes(B, N)) return HSP_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
+  // D = 128: tensor-core filter (tcgen05 + TMEM) + exact FP32 refine, bit-identical results
+  // (knn_feat_tc.cu).  HSP_KNN_FEAT_EXACT=1 forces the all-FP32 kernel below (A/B testing).
+  static const bool force_exact = getenv("HSP_KNN_FEAT_EXACT") != nullptr;
+  if (D == 128 && K <= 32 && N <= 65535 && !force_exact && (((uintptr_t)feat) & 15) == 0)
+    return knn_feat_tc_launch(feat, B, N, K, drop_first, idx64, idx32, workspace, st);
   float* qn = (float*)workspace;
   sqnorm_rows_kernel<<<(B * N + 127) / 128, 128, 0, st>>>(feat, B * N, D, qn);
   HSP_LAUNCH_CHECK();

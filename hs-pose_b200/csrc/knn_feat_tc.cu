@@ -1,0 +1,568 @@
+// K2-TC — feature-space KNN (D = 128) as "tensor-core filter + exact refine".
+//
+// Replaces get_neighbor_index(feature_map, k) (reference gcn3d.py:15-24, RF-F mode of
+// get_receptive_fields gcn3d.py:189-209) for D = 128 with results BIT-IDENTICAL to the exact
+// FP32 kernel (knn_feat.cu) and the oracle:
+//
+//  1. kf_split / kf_norm (pre-pass): every feature row is split into bf16 hi + bf16 lo
+//     (x ~ hi + lo, |residual| <= 2^-18 |x|) and written in UMMA "core-matrix" order
+//     ([64-row tile][16-byte k-chunk][row][8 bf16]); |f|^2 is the exact sequential FP32 sum.
+//  2. knn_feat_tc_kernel: one CTA = 128 query rows of one object.  The query block (hi, lo) and
+//     64-candidate sub-tiles are brought into shared memory by TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx) and multiplied on the 5th-gen tensor cores
+//     (tcgen05.mma kind::f16, M=128 N=64 K=16; hi*hi + hi*lo + lo*hi, FP32 accumulate in TMEM):
+//     up to 512 approximate inner products per row stay resident in TMEM.
+//  3. Epilogue (thread = TMEM lane = query row): approximate distances d~ = q_j - 2*inner~.
+//     32 running "slot minima" give an upper bound tau on the K-th smallest d~; every candidate
+//     with d~ <= tau + 2*eps survives (eps bounds |d~ - d_fp32| from the row norms), ~K+10 of 1028.
+//  4. Refine: for the survivors only, the EXACT sequential-FMA FP32 distance (same expression
+//     and order as knn_feat.cu / oracle) is evaluated and the exact (distance, index) top-K is
+//     taken.  If eps is a valid bound the survivors contain the exact top-K, so the result does
+//     not depend on the tensor-core arithmetic at all.  A row whose survivor list overflows
+//     (massive ties / duplicates) falls back to scanning all candidates exactly.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace hsp {
+namespace tc {
+
+constexpr int TR = 64;                      // rows per global tile
+constexpr int DK = 128;                     // feature dimension of this path
+constexpr int KC = DK / 8;                  // 16-byte k-chunks per row
+constexpr int TILE_BYTES = KC * TR * 16;    // one (tile, hi|lo) block: 16 KB
+constexpr int QROWS = 128;                  // query rows per CTA = UMMA M
+constexpr int ROUND_COLS = 512;             // TMEM columns = candidates resident per round
+constexpr int LCAP = 92;                    // survivor list capacity per row (shared memory, 8 B entries)
+constexpr int SLOTS = 64;                   // running slot minima per row (slot = column mod 64)
+constexpr int SCAP = 64;                    // survivors per row handed to the refine kernel
+constexpr int SPITCH = DK + 4;              // staged candidate row pitch (floats): conflict-free LDS.128
+constexpr int THREADS = 128;
+constexpr float EPS_REL = 1.220703125e-4f;  // 2^-13: |d~ - d_fp32| <= EPS_REL * |f_i| * |f_j|
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 bytes (128 B
+// contiguous); LBO = byte distance between the two k-chunks of one MMA, SBO = between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  return d;                 // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+}
+// Instruction descriptor kind::f16: D = F32, A = B = BF16, both K-major, M x N.
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// two back-to-back 32-column loads, one wait (hides one TMEM round trip)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+  uint32_t r[64];
+#define HSP_TL(o, a)                                                                                                \
+  asm volatile(                                                                                                     \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, " \
+      "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"            \
+      : "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]),          \
+        "=r"(r[o + 6]), "=r"(r[o + 7]), "=r"(r[o + 8]), "=r"(r[o + 9]), "=r"(r[o + 10]), "=r"(r[o + 11]),        \
+        "=r"(r[o + 12]), "=r"(r[o + 13]), "=r"(r[o + 14]), "=r"(r[o + 15]), "=r"(r[o + 16]), "=r"(r[o + 17]),    \
+        "=r"(r[o + 18]), "=r"(r[o + 19]), "=r"(r[o + 20]), "=r"(r[o + 21]), "=r"(r[o + 22]), "=r"(r[o + 23]),    \
+        "=r"(r[o + 24]), "=r"(r[o + 25]), "=r"(r[o + 26]), "=r"(r[o + 27]), "=r"(r[o + 28]), "=r"(r[o + 29]),    \
+        "=r"(r[o + 30]), "=r"(r[o + 31])                                                                           \
+      : "r"(a)                                                                                                      \
+      : "memory")
+  HSP_TL(0, taddr);
+  HSP_TL(32, taddr + 32);
+#undef HSP_TL
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------- pre-pass
+// hi/lo split into the tiled UMMA layout.  One thread = one 16-byte k-chunk of one row.
+__global__ void __launch_bounds__(256)
+kf_split_kernel(const float* __restrict__ feat, int N, int T64, __nv_bfloat16* __restrict__ hi,
+                __nv_bfloat16* __restrict__ lo) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T64 * TR * KC) return;
+  const int row = t / KC, kc = t % KC;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+  if (row < N) {
+    const float4* p = reinterpret_cast<const float4*>(feat + ((size_t)b * N + row) * DK + kc * 8);
+    const float4 a = __ldg(p), c = __ldg(p + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+  }
+  uint4 uh, ul;
+  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&uh);
+  __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&ul);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(h);
+    h2[i] = h;
+    l2[i] = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+  }
+  const size_t off = ((((size_t)b * T64 + row / TR) * KC + kc) * TR + (row % TR)) * 8;
+  *reinterpret_cast<uint4*>(hi + off) = uh;
+  *reinterpret_cast<uint4*>(lo + off) = ul;
+}
+
+// Exact |f|^2 (rounded squares added left to right, as knn_feat.cu) padded with +inf; per-object max.
+__global__ void __launch_bounds__(128)
+kf_norm_kernel(const float* __restrict__ feat, int N, int rows_pad, float* __restrict__ qn,
+               float* __restrict__ qmax) {
+  const int b = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows_pad) return;
+  float s = INFINITY;
+  if (r < N) {
+    const float4* p = reinterpret_cast<const float4*>(feat + ((size_t)b * N + r) * DK);
+    s = 0.0f;
+#pragma unroll 4
+    for (int d4 = 0; d4 < DK / 4; ++d4) {
+      const float4 v = __ldg(p + d4);
+      if (d4 == 0) s = __fmul_rn(v.x, v.x); else s = __fadd_rn(s, __fmul_rn(v.x, v.x));
+      s = __fadd_rn(s, __fmul_rn(v.y, v.y));
+      s = __fadd_rn(s, __fmul_rn(v.z, v.z));
+      s = __fadd_rn(s, __fmul_rn(v.w, v.w));
+    }
+    if (s == s) atomicMax(reinterpret_cast<int*>(qmax + b), __float_as_int(s));   // s >= 0: int order = float order
+  }
+  qn[(size_t)b * rows_pad + r] = s;
+}
+
+// Thread-private ascending sort of NS registers (bitonic network, compile-time indices).
+template <int NS>
+__device__ __forceinline__ void sort_regs(float (&m)[NS]) {
+#pragma unroll
+  for (int k = 2; k <= NS; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool asc = ((i & k) == 0);
+          const float a = m[i], c = m[l];
+          m[i] = asc ? fminf(a, c) : fmaxf(a, c);
+          m[l] = asc ? fmaxf(a, c) : fminf(a, c);
+        }
+      }
+    }
+  }
+}
+
+// exact FP32 distance of the reference formula, one sequential FMA chain over d (knn_feat.cu order);
+// fi: query row (global, warp-uniform -> broadcast), sj: candidate row staged in shared memory
+__device__ __forceinline__ float exact_dist(const float* __restrict__ fi, const float* sj, float qi, float qj) {
+  const float4* a4 = reinterpret_cast<const float4*>(fi);
+  const float4* b4 = reinterpret_cast<const float4*>(sj);
+  float acc = 0.0f;
+#pragma unroll 8
+  for (int d4 = 0; d4 < DK / 4; ++d4) {
+    const float4 a = __ldg(a4 + d4), c = b4[d4];
+    acc = __fmaf_rn(a.x, c.x, acc);
+    acc = __fmaf_rn(a.y, c.y, acc);
+    acc = __fmaf_rn(a.z, c.z, acc);
+    acc = __fmaf_rn(a.w, c.w, acc);
+  }
+  return __fadd_rn(__fadd_rn(__fmul_rn(acc, -2.0f), qj), qi);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+knn_feat_tc_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* __restrict__ glo,
+                   const float* __restrict__ qn, const float* __restrict__ qmax, int N, int T64, int K,
+                   uint16_t* __restrict__ surv_idx, int* __restrict__ surv_cnt) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sA_hi = smem;                                   // [KC][128][8] bf16   32 KB
+  unsigned char* sA_lo = sA_hi + 2 * TILE_BYTES;                 //                      32 KB
+  unsigned char* sB = sA_lo + 2 * TILE_BYTES;                    // 2 stages x (hi 16 KB + lo 16 KB)
+  float* s_qn = reinterpret_cast<float*>(sB + 4 * TILE_BYTES);   // [ROUND_COLS]
+  uint2* s_list = reinterpret_cast<uint2*>(s_qn + ROUND_COLS);   // [128][LCAP] (approximate distance bits, index)
+  int* s_cnt = reinterpret_cast<int*>(s_list + QROWS * LCAP);    // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_cnt + QROWS);   // [0..1] full, [2..3] empty, [4] A, [5] round done
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int b = blockIdx.y, qt = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rows_pad = T64 * TR;
+  const unsigned char* obj_hi = reinterpret_cast<const unsigned char*>(ghi) + (size_t)b * T64 * TILE_BYTES;
+  const unsigned char* obj_lo = reinterpret_cast<const unsigned char*>(glo) + (size_t)b * T64 * TILE_BYTES;
+  const float* qb = qn + (size_t)b * rows_pad;
+
+  if (warp == 0) {   // TMEM: all 512 columns (one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) mbar_init(bars + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  s_cnt[tid] = 0;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *s_tmem;
+
+  // query block: two 64-row tiles -> [KC][128][8]   (64 bulk copies of 1 KB)
+  if (tid == 0) {
+    mbar_expect_tx(bars + 4, 4 * TILE_BYTES);
+    for (int h = 0; h < 2; ++h) {
+      const size_t src = (size_t)(2 * qt + h) * TILE_BYTES;
+      for (int kc = 0; kc < KC; ++kc) {
+        bulk_g2s(sA_hi + kc * 2048 + h * 1024, obj_hi + src + kc * 1024, 1024, bars + 4);
+        bulk_g2s(sA_lo + kc * 2048 + h * 1024, obj_lo + src + kc * 1024, 1024, bars + 4);
+      }
+    }
+  }
+
+  const int i_row = qt * QROWS + tid;                 // this thread's query row (TMEM lane tid)
+  const bool row_ok = i_row < N;
+  const float qi = qb[min(i_row, rows_pad - 1)];
+  const float eps2 = 2.0f * EPS_REL * sqrtf(fmaxf(qi, 0.0f) * __ldg(qmax + b)) + 1e-30f;
+  float thr = INFINITY;                               // running upper bound on the K-th smallest (d~ - qi)
+  int cnt = 0;
+  bool overflow = false;
+  float m[SLOTS];                                     // running slot minima of d~ - qi
+#pragma unroll
+  for (int i = 0; i < SLOTS; ++i) m[i] = INFINITY;
+
+  const uint32_t idesc = umma_idesc(QROWS, TR);
+  const int nsub_total = T64;                         // 64-candidate sub-tiles
+  int it = 0;                                         // global sub-tile counter (pipeline phase tracking)
+  for (int sub0 = 0, round = 0; sub0 < nsub_total; sub0 += ROUND_COLS / TR, ++round) {
+    const int nsub = min(ROUND_COLS / TR, nsub_total - sub0);
+    const int col0 = sub0 * TR;
+    // candidate norms of this round
+    for (int c = tid; c < nsub * TR; c += THREADS) s_qn[c] = qb[col0 + c];
+
+    if (tid == 0) {
+      if (round == 0) mbar_wait(bars + 4, 0);
+      auto load = [&](int s, int iter) {
+        const int st = iter & 1;
+        if (iter >= 2) mbar_wait(bars + 2 + st, ((iter >> 1) - 1) & 1);   // MMAs that read this stage are done
+        mbar_expect_tx(bars + st, 2 * TILE_BYTES);
+        bulk_g2s(sB + st * 2 * TILE_BYTES, obj_hi + (size_t)(sub0 + s) * TILE_BYTES, TILE_BYTES, bars + st);
+        bulk_g2s(sB + st * 2 * TILE_BYTES + TILE_BYTES, obj_lo + (size_t)(sub0 + s) * TILE_BYTES, TILE_BYTES,
+                 bars + st);
+      };
+      load(0, it);
+      for (int s = 0; s < nsub; ++s) {
+        const int iter = it + s, st = iter & 1;
+        if (s + 1 < nsub) load(s + 1, iter + 1);
+        mbar_wait(bars + st, (iter >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(s * TR);
+        const uint32_t bh = smem_u32(sB + st * 2 * TILE_BYTES), bl = bh + TILE_BYTES;
+        const uint32_t ah = smem_u32(sA_hi), al = smem_u32(sA_lo);
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t a0 = term == 2 ? al : ah, b0 = term == 1 ? bl : bh;
+#pragma unroll
+          for (int k = 0; k < DK / 16; ++k)
+            umma_bf16(d_tmem, umma_desc(a0 + k * 2 * 2048, 2048, 128), umma_desc(b0 + k * 2 * 1024, 1024, 128),
+                      idesc, (term | k) != 0);
+        }
+        umma_commit(bars + 2 + st);                 // stage free when these MMAs retire
+        if (s == nsub - 1) umma_commit(bars + 5);   // round complete
+      }
+    }
+    it += nsub;
+    __syncthreads();                                  // s_qn visible; (tid 0 has issued everything)
+    mbar_wait(bars + 5, round & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: thread = TMEM lane = query row
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const float4* s_qn4 = reinterpret_cast<const float4*>(s_qn);
+    if (round == 0) {
+      // first round: one pass for the slot minima (slot = column mod 32), threshold, second pass below
+      for (int c = 0; c < nsub * TR; c += 64) {
+        float v[64];
+        tmem_ld64(t_row + (uint32_t)c, v);
+#pragma unroll
+        for (int i4 = 0; i4 < 16; ++i4) {
+          const float4 q4 = s_qn4[(c >> 2) + i4];
+          m[4 * i4] = fminf(m[4 * i4], fmaf(-2.0f, v[4 * i4], q4.x));
+          m[4 * i4 + 1] = fminf(m[4 * i4 + 1], fmaf(-2.0f, v[4 * i4 + 1], q4.y));
+          m[4 * i4 + 2] = fminf(m[4 * i4 + 2], fmaf(-2.0f, v[4 * i4 + 2], q4.z));
+          m[4 * i4 + 3] = fminf(m[4 * i4 + 3], fmaf(-2.0f, v[4 * i4 + 3], q4.w));
+        }
+      }
+      float ms[SLOTS];
+#pragma unroll
+      for (int i = 0; i < SLOTS; ++i) ms[i] = m[i];
+      sort_regs<SLOTS>(ms);
+      float tau = ms[0];
+#pragma unroll
+      for (int i = 1; i < 32; ++i) tau = (i == K - 1) ? ms[i] : tau;
+      thr = tau;                       // >= K distinct candidates lie at or below it
+    }
+    // survivors under the best threshold known when the round starts; later rounds update the slot
+    // minima in the same pass (the list is re-filtered with the final threshold at the end).  The
+    // TMEM loads are .sync.aligned: every lane runs the same loop; rows past N collect nothing.
+    // Padding columns carry q = +inf and never pass a finite limit; NaN distances always pass.
+    const float lim = row_ok ? thr + eps2 : -INFINITY;
+    uint2* my_list = s_list + tid * LCAP;
+    for (int c = 0; c < nsub * TR; c += 64) {
+      float v[64];
+      tmem_ld64(t_row + (uint32_t)c, v);
+      const int jb = col0 + c;
+      bool room = true;
+#pragma unroll
+      for (int i4 = 0; i4 < 16; ++i4) {
+        if ((i4 & 3) == 0) {                        // 16 columns append at most 16: one capacity check
+          room = cnt <= LCAP - 16;
+          overflow |= !room;
+        }
+        const float4 q4 = s_qn4[(c >> 2) + i4];
+        const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = 4 * i4 + u;
+          const float dapp = fmaf(-2.0f, v[i], qv[u]);
+          if (round != 0) m[i] = fminf(m[i], dapp);
+          if (room && !(dapp > lim)) {
+            my_list[cnt] = make_uint2(__float_as_uint(dapp), (unsigned)(jb + i));
+            ++cnt;
+          }
+        }
+      }
+    }
+    if (round != 0) {
+      float ms[SLOTS];
+#pragma unroll
+      for (int i = 0; i < SLOTS; ++i) ms[i] = m[i];
+      sort_regs<SLOTS>(ms);
+      float tau = ms[0];
+#pragma unroll
+      for (int i = 1; i < 32; ++i) tau = (i == K - 1) ? ms[i] : tau;
+      thr = fminf(thr, tau);
+    }
+    if (cnt > 40 && !overflow) {   // keep the list short: re-filter with the tightened threshold
+      const float lim2 = thr + eps2;
+      int w = 0;
+      for (int e = 0; e < cnt; ++e) {
+        const uint2 ev = my_list[e];
+        if (!(__uint_as_float(ev.x) > lim2)) { my_list[w] = ev; ++w; }
+      }
+      cnt = w;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                                  // TMEM / s_qn free for the next round
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  // final threshold is the tightest: drop survivors of earlier rounds that no longer qualify, and
+  // compact the indices to 16 bits in place (entry w is written after entry e >= w was read)
+  {
+    const float lim = thr + eps2;
+    uint2* my_list = s_list + tid * LCAP;
+    uint16_t* my_idx = reinterpret_cast<uint16_t*>(my_list);
+    int w = 0;
+    for (int e = 0; e < cnt; ++e) {
+      const uint2 ev = my_list[e];
+      if (!(__uint_as_float(ev.x) > lim)) { my_idx[w] = (uint16_t)ev.y; ++w; }
+    }
+    cnt = w;
+  }
+  if (overflow || cnt > SCAP) cnt = -1;              // refine scans every candidate for this row
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  if (row_ok) {
+    surv_cnt[(size_t)b * N + i_row] = cnt;
+    const uint4* src = reinterpret_cast<const uint4*>(s_list + tid * LCAP);   // 16-bit indices, compacted above
+    uint4* dst = reinterpret_cast<uint4*>(surv_idx + ((size_t)b * N + i_row) * SCAP);
+#pragma unroll
+    for (int e = 0; e < SCAP * 2 / 16; ++e) dst[e] = src[e];
+  }
+}
+
+// ---- refine: warp per query row.  The survivors' FP32 rows are fetched cooperatively (a warp reads
+// one 512-byte row with four coalesced 128-byte requests; all rows of a batch in flight) into
+// shared memory, lane l runs the exact sequential chain for survivor l, the warp sorts the exact
+// (distance, index) keys.  Rows flagged -1 scan every candidate.
+constexpr int RF_WARPS = 8;
+constexpr int RF_Q = 32;                    // features staged per pass (a quarter row)
+constexpr int RF_PITCH = RF_Q + 4;
+template <int NL>
+__global__ void __launch_bounds__(RF_WARPS * 32)
+kf_refine_kernel(const float* __restrict__ feat, const float* __restrict__ qn, const uint16_t* __restrict__ surv_idx,
+                 const int* __restrict__ surv_cnt, int N, int rows_pad, int K, int drop,
+                 int64_t* __restrict__ idx64, int32_t* __restrict__ idx32) {
+  __shared__ __align__(16) float s_stage[RF_WARPS][32 * RF_PITCH];
+  __shared__ uint64_t s_queue[RF_WARPS * 64];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * RF_WARPS + warp;
+  if (i >= N) return;
+  const float* fb = feat + (size_t)b * N * DK;
+  const float* qb = qn + (size_t)b * rows_pad;
+  const float4* a4 = reinterpret_cast<const float4*>(fb + (size_t)i * DK);
+  const float q_i = qb[i];
+  float* stage = s_stage[warp];
+  const int c_r = surv_cnt[(size_t)b * N + i];
+  const uint16_t* li = surv_idx + ((size_t)b * N + i) * SCAP;
+  const int total = c_r >= 0 ? c_r : N;
+  const int sub = lane >> 3, l8 = lane & 7;           // 4 rows per fetch instruction, 8 lanes x 16 B each
+  WarpTopK<NL> top;
+  top.reset(s_queue + warp * 64);
+  for (int base = 0; base < total; base += 32) {
+    const int nb = min(32, total - base);
+    int jl = lane < nb ? (c_r >= 0 ? (int)li[base + lane] : base + lane) : 0;
+    jl = min(jl, N - 1);
+    float acc = 0.0f;
+    for (int qd = 0; qd < DK; qd += RF_Q) {
+      __syncwarp();
+      float4 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {      // rows 4u + sub: a warp request covers four 128-byte row pieces
+        const int j = __shfl_sync(0xffffffffu, jl, 4 * u + sub);
+        t[u] = __ldg(reinterpret_cast<const float4*>(fb + (size_t)j * DK + qd) + l8);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<float4*>(stage + (4 * u + sub) * RF_PITCH + 4 * l8) = t[u];
+      __syncwarp();
+      const float4* b4 = reinterpret_cast<const float4*>(stage + lane * RF_PITCH);
+#pragma unroll
+      for (int d4 = 0; d4 < RF_Q / 4; ++d4) {   // continues ONE sequential FMA chain over d
+        const float4 a = __ldg(a4 + (qd >> 2) + d4), c = b4[d4];
+        acc = __fmaf_rn(a.x, c.x, acc);
+        acc = __fmaf_rn(a.y, c.y, acc);
+        acc = __fmaf_rn(a.z, c.z, acc);
+        acc = __fmaf_rn(a.w, c.w, acc);
+      }
+    }
+    uint64_t key = KEY_MAX;
+    if (lane < nb)
+      key = make_key(__fadd_rn(__fadd_rn(__fmul_rn(acc, -2.0f), qb[jl]), q_i), (uint32_t)jl);
+    if (c_r >= 0 || __any_sync(0xffffffffu, key < top.thr)) top.merge(key, lane, K);
+  }
+  const int k_out = K - drop;
+  const size_t o = ((size_t)b * N + i) * k_out;
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    const int rank = l * 32 + lane - drop;
+    if (rank >= 0 && rank < k_out) {
+      const uint32_t j = (uint32_t)(top.L[l] & 0xffffffffu);
+      if (idx64) idx64[o + rank] = (int64_t)j;
+      if (idx32) idx32[o + rank] = (int32_t)j;
+    }
+  }
+}
+
+static size_t smem_bytes() {
+  return (size_t)8 * TILE_BYTES + ROUND_COLS * sizeof(float) + (size_t)QROWS * LCAP * sizeof(uint2) +
+         QROWS * sizeof(int) + 6 * sizeof(uint64_t) + 16;
+}
+
+}  // namespace tc
+
+// T64: number of 64-row tiles, rounded up to an even count (a query block is two tiles).
+static int kf_tc_tiles(int N) { return 2 * ((N + 127) / 128); }
+
+size_t knn_feat_tc_workspace_bytes(int B, int N) {
+  const size_t T64 = kf_tc_tiles(N);
+  return (size_t)B * T64 * tc::TILE_BYTES * 2 + (size_t)B * T64 * tc::TR * sizeof(float) + (size_t)B * sizeof(float) +
+         (size_t)B * N * (tc::SCAP * sizeof(uint16_t) + sizeof(int)) + 1024;
+}
+
+// D = 128, K = k + drop <= 32, N <= 65535.
+int knn_feat_tc_launch(const float* feat, int B, int N, int K, int drop, int64_t* idx64, int32_t* idx32,
+                       void* workspace, cudaStream_t st) {
+  using namespace tc;
+  const int T64 = kf_tc_tiles(N);
+  unsigned char* ws = (unsigned char*)workspace;
+  ws = (unsigned char*)(((uintptr_t)ws + 127) & ~(uintptr_t)127);
+  __nv_bfloat16* hi = (__nv_bfloat16*)ws;
+  __nv_bfloat16* lo = (__nv_bfloat16*)(ws + (size_t)B * T64 * TILE_BYTES);
+  float* qn = (float*)(ws + (size_t)B * T64 * TILE_BYTES * 2);
+  float* qmax = qn + (size_t)B * T64 * TR;
+  uintptr_t p = ((uintptr_t)(qmax + B) + 127) & ~(uintptr_t)127;
+  uint16_t* surv_idx = (uint16_t*)p;
+  int* surv_cnt = (int*)(p + (size_t)B * N * SCAP * sizeof(uint16_t));
+  if (cudaMemsetAsync(qmax, 0, sizeof(float) * B, st) != cudaSuccess) return HSP_ELAUNCH;
+  kf_norm_kernel<<<dim3((T64 * TR + 127) / 128, B), 128, 0, st>>>(feat, N, T64 * TR, qn, qmax);
+  HSP_LAUNCH_CHECK();
+  kf_split_kernel<<<dim3((T64 * TR * KC + 255) / 256, B), 256, 0, st>>>(feat, N, T64, hi, lo);
+  HSP_LAUNCH_CHECK();
+  const size_t smem = smem_bytes();
+  if (cudaFuncSetAttribute(knn_feat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+      cudaSuccess)
+    return HSP_ELAUNCH;
+  knn_feat_tc_kernel<<<dim3(T64 / 2, B), THREADS, smem, st>>>(hi, lo, qn, qmax, N, T64, K, surv_idx, surv_cnt);
+  HSP_LAUNCH_CHECK();
+  kf_refine_kernel<1><<<dim3((N + RF_WARPS - 1) / RF_WARPS, B), RF_WARPS * 32, 0, st>>>(
+      feat, qn, surv_idx, surv_cnt, N, T64 * TR, K, drop, idx64, idx32);
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}
+
+}  // namespace hsp
