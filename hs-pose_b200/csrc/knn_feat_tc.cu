@@ -35,10 +35,16 @@ constexpr int QROWS = 128;                  // query rows per CTA = UMMA M
 constexpr int ROUND_COLS = 512;             // TMEM columns = candidates resident per round
 constexpr int LCAP = 92;                    // survivor list capacity per row (shared memory, 8 B entries)
 constexpr int SLOTS = 64;                   // running slot minima per row (slot = column mod 64)
-constexpr int SCAP = 64;                    // survivors per row handed to the refine kernel
+constexpr int SCAP = 96;                    // survivors per row handed to the refine kernel
 constexpr int SPITCH = DK + 4;              // staged candidate row pitch (floats): conflict-free LDS.128
 constexpr int THREADS = 128;
-constexpr float EPS_REL = 1.220703125e-4f;  // 2^-13: |d~ - d_fp32| <= EPS_REL * |f_i| * |f_j|
+// |d~ - d_fp32| <= EPS_REL * |f_i| * |f_j|.  Budget (units of |f_i||f_j|, x2 for the -2*inner factor):
+// dropped lo*lo and residual terms of the bf16 split 3 * 2^-18 = 1.1e-5; FP32 accumulator rounding of the
+// 24 MMA updates (16 exact bf16 products each) 24 * 2^-23 = 2.9e-6; the exact kernel's own sequential
+// FP32 chain 128 * 2^-24 = 7.6e-6  ->  2 * 2.2e-5 = 4.3e-5 < 2^-14 = 6.1e-5.  The split term is checked
+// on the reference's feature maps in tests/test_oracle_golden.py; every -m gpu KNN test compares the
+// final indices bit for bit with the exact FP32 oracle.
+constexpr float EPS_REL = 6.103515625e-5f;
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -342,8 +348,9 @@ knn_feat_tc_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* _
     // ---- epilogue: thread = TMEM lane = query row
     const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
     const float4* s_qn4 = reinterpret_cast<const float4*>(s_qn);
-    if (round == 0) {
-      // first round: one pass for the slot minima (slot = column mod 32), threshold, second pass below
+    uint2* my_list = s_list + tid * LCAP;
+    {
+      // pass 1: running slot minima over every candidate seen so far (slot = column mod 64)
       for (int c = 0; c < nsub * TR; c += 64) {
         float v[64];
         tmem_ld64(t_row + (uint32_t)c, v);
@@ -363,14 +370,21 @@ knn_feat_tc_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* _
       float tau = ms[0];
 #pragma unroll
       for (int i = 1; i < 32; ++i) tau = (i == K - 1) ? ms[i] : tau;
-      thr = tau;                       // >= K distinct candidates lie at or below it
+      thr = fminf(thr, tau);           // >= K distinct candidates lie at or below it
     }
-    // survivors under the best threshold known when the round starts; later rounds update the slot
-    // minima in the same pass (the list is re-filtered with the final threshold at the end).  The
+    if (cnt > 24 && !overflow) {       // survivors of earlier rounds under the tightened threshold
+      const float lim2 = thr + eps2;
+      int w = 0;
+      for (int e = 0; e < cnt; ++e) {
+        const uint2 ev = my_list[e];
+        if (!(__uint_as_float(ev.x) > lim2)) { my_list[w] = ev; ++w; }
+      }
+      cnt = w;
+    }
+    // pass 2 over the resident inner products: survivors under the tightest threshold known.  The
     // TMEM loads are .sync.aligned: every lane runs the same loop; rows past N collect nothing.
     // Padding columns carry q = +inf and never pass a finite limit; NaN distances always pass.
     const float lim = row_ok ? thr + eps2 : -INFINITY;
-    uint2* my_list = s_list + tid * LCAP;
     for (int c = 0; c < nsub * TR; c += 64) {
       float v[64];
       tmem_ld64(t_row + (uint32_t)c, v);
@@ -388,32 +402,12 @@ knn_feat_tc_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* _
         for (int u = 0; u < 4; ++u) {
           const int i = 4 * i4 + u;
           const float dapp = fmaf(-2.0f, v[i], qv[u]);
-          if (round != 0) m[i] = fminf(m[i], dapp);
           if (room && !(dapp > lim)) {
             my_list[cnt] = make_uint2(__float_as_uint(dapp), (unsigned)(jb + i));
             ++cnt;
           }
         }
       }
-    }
-    if (round != 0) {
-      float ms[SLOTS];
-#pragma unroll
-      for (int i = 0; i < SLOTS; ++i) ms[i] = m[i];
-      sort_regs<SLOTS>(ms);
-      float tau = ms[0];
-#pragma unroll
-      for (int i = 1; i < 32; ++i) tau = (i == K - 1) ? ms[i] : tau;
-      thr = fminf(thr, tau);
-    }
-    if (cnt > 40 && !overflow) {   // keep the list short: re-filter with the tightened threshold
-      const float lim2 = thr + eps2;
-      int w = 0;
-      for (int e = 0; e < cnt; ++e) {
-        const uint2 ev = my_list[e];
-        if (!(__uint_as_float(ev.x) > lim2)) { my_list[w] = ev; ++w; }
-      }
-      cnt = w;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();                                  // TMEM / s_qn free for the next round

@@ -110,3 +110,21 @@ def test_fused_ops_oracles_match_reference(golden):
     buf = np.zeros((B, N, C + 3), np.float32)
     co.upsample_rows_fwd(g["pool_feat"], nn[..., 0], buf, 3)
     np.testing.assert_array_equal(buf[..., 3:], g["up_out"])
+
+
+def test_bf16_split_error_budget_of_the_tensor_core_filter(golden):
+    """K2-TC (csrc/knn_feat_tc.cu) ranks candidates with hi*hi + hi*lo + lo*hi of a bf16 hi/lo split and
+    keeps everything within 2*eps of its threshold, eps = 2^-14 * |f_i||f_j|.  The split part of that
+    budget (3 * 2^-18 per product) is checked here on the reference's own feature maps: the dropped
+    terms stay far below the bound, so the survivors provably contain the exact top-k."""
+    import torch
+    g = golden("knn")
+    f = torch.from_numpy(g["f128"][0]).double()
+    hi = f.float().to(torch.bfloat16).double()
+    lo = (f - hi).float().to(torch.bfloat16).double()
+    exact = f @ f.t()
+    approx = hi @ hi.t() + hi @ lo.t() + lo @ hi.t()
+    nrm = f.norm(dim=1)
+    rel = ((exact - approx).abs() / (nrm[:, None] * nrm[None, :])).max().item()
+    assert rel < 3 * 2.0 ** -18, rel          # the analytic bound on the dropped terms
+    assert rel < 2.0 ** -14 / 8, rel          # and 8x below the total budget the kernel uses
