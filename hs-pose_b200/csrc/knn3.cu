@@ -268,8 +268,8 @@ extern "C" int hsp_knn3(const float* query, const float* cand, int B, int M, int
       return dispatch_knn3_reg<1, HSP_DIST_NEIGHBOR>(query, cand, B, M, N, K, drop_first, idx64, idx32, st);
     return dispatch_knn3_reg<1, HSP_DIST_NEAREST>(query, cand, B, M, N, K, drop_first, idx64, idx32, st);
   }
-  // K in (32, 64]: the streaming kernel (two sorted registers per lane)
+  // K in (32, 64]: two sorted registers per lane
   if (formula == HSP_DIST_NEIGHBOR)
-    return launch_knn3<2, HSP_DIST_NEIGHBOR>(query, cand, B, M, N, K, drop_first, idx64, idx32, st);
-  return launch_knn3<2, HSP_DIST_NEAREST>(query, cand, B, M, N, K, drop_first, idx64, idx32, st);
+    return dispatch_knn3_reg<2, HSP_DIST_NEIGHBOR>(query, cand, B, M, N, K, drop_first, idx64, idx32, st);
+  return dispatch_knn3_reg<2, HSP_DIST_NEAREST>(query, cand, B, M, N, K, drop_first, idx64, idx32, st);
 }

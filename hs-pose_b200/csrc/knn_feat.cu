@@ -291,7 +291,7 @@ extern "C" int hsp_knn_feat(const float* feat, int B, int N, int D, int k, int d
   // D = 128: tensor-core filter (tcgen05 + TMEM) + exact FP32 refine, bit-identical results
   // (knn_feat_tc.cu).  HSP_KNN_FEAT_EXACT=1 forces the all-FP32 kernel below (A/B testing).
   static const bool force_exact = getenv("HSP_KNN_FEAT_EXACT") != nullptr;
-  if (D == 128 && K <= 32 && N <= 65535 && !force_exact && (((uintptr_t)feat) & 15) == 0)
+  if (D == 128 && K <= 64 && N <= 65535 && !force_exact && (((uintptr_t)feat) & 15) == 0)
     return knn_feat_tc_launch(feat, B, N, K, drop_first, idx64, idx32, workspace, st);
   float* qn = (float*)workspace;
   sqnorm_rows_kernel<<<(B * N + 127) / 128, 128, 0, st>>>(feat, B * N, D, qn);

@@ -369,7 +369,7 @@ knn_feat_tc_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* _
       sort_regs<SLOTS>(ms);
       float tau = ms[0];
 #pragma unroll
-      for (int i = 1; i < 32; ++i) tau = (i == K - 1) ? ms[i] : tau;
+      for (int i = 1; i < SLOTS; ++i) tau = (i == K - 1) ? ms[i] : tau;
       thr = fminf(thr, tau);           // >= K distinct candidates lie at or below it
     }
     if (cnt > 24 && !overflow) {       // survivors of earlier rounds under the tightened threshold
@@ -528,7 +528,7 @@ size_t knn_feat_tc_workspace_bytes(int B, int N) {
          (size_t)B * N * (tc::SCAP * sizeof(uint16_t) + sizeof(int)) + 1024;
 }
 
-// D = 128, K = k + drop <= 32, N <= 65535.
+// D = 128, K = k + drop <= 64, N <= 65535.
 int knn_feat_tc_launch(const float* feat, int B, int N, int K, int drop, int64_t* idx64, int32_t* idx32,
                        void* workspace, cudaStream_t st) {
   using namespace tc;
@@ -553,8 +553,12 @@ int knn_feat_tc_launch(const float* feat, int B, int N, int K, int drop, int64_t
     return HSP_ELAUNCH;
   knn_feat_tc_kernel<<<dim3(T64 / 2, B), THREADS, smem, st>>>(hi, lo, qn, qmax, N, T64, K, surv_idx, surv_cnt);
   HSP_LAUNCH_CHECK();
-  kf_refine_kernel<1><<<dim3((N + RF_WARPS - 1) / RF_WARPS, B), RF_WARPS * 32, 0, st>>>(
-      feat, qn, surv_idx, surv_cnt, N, T64 * TR, K, drop, idx64, idx32);
+  if (K <= 32)
+    kf_refine_kernel<1><<<dim3((N + RF_WARPS - 1) / RF_WARPS, B), RF_WARPS * 32, 0, st>>>(
+        feat, qn, surv_idx, surv_cnt, N, T64 * TR, K, drop, idx64, idx32);
+  else
+    kf_refine_kernel<2><<<dim3((N + RF_WARPS - 1) / RF_WARPS, B), RF_WARPS * 32, 0, st>>>(
+        feat, qn, surv_idx, surv_cnt, N, T64 * TR, K, drop, idx64, idx32);
   HSP_LAUNCH_CHECK();
   return HSP_OK;
 }
