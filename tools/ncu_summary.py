@@ -49,6 +49,17 @@ for n, r in enumerate(data):
         g(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
         g(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
         g(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0)))
+# machine-readable DRAM traffic per launch (bench.py's roofline.traffic reads profiles/kernel_traffic.json)
+import json
+traffic = []
+for r in data:
+    name = re.sub(r"\(.*$", "", r[col["Kernel Name"]]).replace("void ", "")
+    traffic.append({"kernel": name, "grid": r[col["Grid Size"]], "block": r[col["Block Size"]],
+                    "dram_bytes": (to_mb(g(r, "dram__bytes_read.sum"), unit("dram__bytes_read.sum")) +
+                                   to_mb(g(r, "dram__bytes_write.sum"), unit("dram__bytes_write.sum"))) * 1e6,
+                    "duration_us": to_us(g(r, "gpu__time_duration.sum"), unit("gpu__time_duration.sum"))})
+if len(sys.argv) > 3:
+    json.dump(traffic, open(sys.argv[3], "w"), indent=1)
 txt = "\n".join(out) + "\n"
 if len(sys.argv) > 2:
     open(sys.argv[2], "w").write(txt)
