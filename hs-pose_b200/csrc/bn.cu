@@ -85,8 +85,12 @@ static BnGeom bn_geom(int M, int C) {
 }
 
 // Two accumulators per channel: A = sum a_i, Bq = sum b_i, where
-//   MODE 0 (forward stats) : a = x,  b = x*x
-//   MODE 1 (backward)      : a = dy', b = dy' * xhat,  dy' = relu-masked dy
+//   MODE 0 (forward stats) : a = x,   b = x*x
+//   MODE 1 (backward)      : a = dy', b = dy' * x,  dy' = relu-masked dy (mask = the forward's own
+//                            y = fma(x, scale, shift) <= 0); dgamma = invstd * (Bq - mean * A) is
+//                            formed in the finalize, so no per-element normalisation is needed here.
+// Four rows are in flight per thread (8 x 16-byte loads): these kernels are pure HBM streams and
+// need the bytes in flight more than they need occupancy.
 template <typename T, int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_reduce_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, int lddy,
@@ -99,30 +103,48 @@ bn_reduce_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, int
   const int c0 = (blockIdx.x * ct + col) * BN_VEC;
   const int rows_per = (M + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
-  float A[BN_VEC], Bq[BN_VEC], mu[BN_VEC], is[BN_VEC], ga[BN_VEC], be[BN_VEC];
+  float A[BN_VEC], Bq[BN_VEC], sc[BN_VEC], sh[BN_VEC];
 #pragma unroll
   for (int i = 0; i < BN_VEC; ++i) {
     A[i] = Bq[i] = 0.f;
-    if (MODE == 1) {
-      mu[i] = mean[c0 + i]; is[i] = invstd[c0 + i];
-      ga[i] = gamma ? gamma[c0 + i] : 1.f; be[i] = beta ? beta[c0 + i] : 0.f;
+    sc[i] = 0.f; sh[i] = 1.f;                    // mask never fires without ReLU
+    if (MODE == 1 && relu) {
+      const float ga = gamma ? gamma[c0 + i] : 1.f, be = beta ? beta[c0 + i] : 0.f;
+      sc[i] = ga * invstd[c0 + i];               // same expressions as bn_finalize_fwd_kernel
+      sh[i] = be - mean[c0 + i] * ga * invstd[c0 + i];
     }
   }
-#pragma unroll 2
-  for (int r = r0 + rlane; r < r1; r += rl) {
-    float xv[BN_VEC];
-    Vec8<T>::load(x + (size_t)r * ldx + c0, xv);
-    if (MODE == 0) {
+  int r = r0 + rlane;
+  for (; r + 3 * rl < r1; r += 4 * rl) {
+    float xv[4][BN_VEC], gv[4][BN_VEC];
 #pragma unroll
-      for (int i = 0; i < BN_VEC; ++i) { A[i] += xv[i]; Bq[i] = fmaf(xv[i], xv[i], Bq[i]); }
-    } else {
-      float gv[BN_VEC];
-      Vec8<T>::load(dy + (size_t)r * lddy + c0, gv);
+    for (int u = 0; u < 4; ++u) {
+      Vec8<T>::load(x + (size_t)(r + u * rl) * ldx + c0, xv[u]);
+      if (MODE == 1) Vec8<T>::load(dy + (size_t)(r + u * rl) * lddy + c0, gv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int i = 0; i < BN_VEC; ++i) {
-        const float xh = (xv[i] - mu[i]) * is[i];
-        const float g = (relu && fmaf(xh, ga[i], be[i]) <= 0.f) ? 0.f : gv[i];
-        A[i] += g; Bq[i] = fmaf(g, xh, Bq[i]);
+        if (MODE == 0) {
+          A[i] += xv[u][i]; Bq[i] = fmaf(xv[u][i], xv[u][i], Bq[i]);
+        } else {
+          const float g = fmaf(xv[u][i], sc[i], sh[i]) <= 0.f ? 0.f : gv[u][i];
+          A[i] += g; Bq[i] = fmaf(g, xv[u][i], Bq[i]);
+        }
+      }
+  }
+  for (; r < r1; r += rl) {
+    float xv[BN_VEC], gv[BN_VEC];
+    Vec8<T>::load(x + (size_t)r * ldx + c0, xv);
+    if (MODE == 1) Vec8<T>::load(dy + (size_t)r * lddy + c0, gv);
+#pragma unroll
+    for (int i = 0; i < BN_VEC; ++i) {
+      if (MODE == 0) {
+        A[i] += xv[i]; Bq[i] = fmaf(xv[i], xv[i], Bq[i]);
+      } else {
+        const float g = fmaf(xv[i], sc[i], sh[i]) <= 0.f ? 0.f : gv[i];
+        A[i] += g; Bq[i] = fmaf(g, xv[i], Bq[i]);
       }
     }
   }
@@ -197,15 +219,17 @@ bn_finalize_fwd_kernel(const float* __restrict__ partial, int rchunks, int M, in
   }
 }
 
-// Backward finalize: dgamma = sum dy' xhat, dbeta = sum dy'.
+// Backward finalize: dbeta = sum dy', dgamma = sum dy' xhat = invstd * (sum dy' x - mean * sum dy').
+// mean == NULL: plain column sums (first plane -> dbeta, second -> dgamma).
 __global__ void __launch_bounds__(BN_FC * BN_FG)
 bn_finalize_bwd_kernel(const float* __restrict__ partial, int rchunks, int C,
+                       const float* __restrict__ mean, const float* __restrict__ invstd,
                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
   int c;
   double s, q;
   if (!bn_sum_partials(partial, rchunks, C, c, s, q)) return;
   dbeta[c] = (float)s;
-  dgamma[c] = (float)q;
+  dgamma[c] = mean ? (float)((double)invstd[c] * (q - (double)mean[c] * s)) : (float)q;
 }
 
 // y = relu?(x * scale + shift)
@@ -235,7 +259,9 @@ bn_apply_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scal
   }
 }
 
-// dx = gamma*invstd * (dy' - dbeta/M - xhat * dgamma/M)
+// dx = gamma*invstd * (dy' - dbeta/M - xhat * dgamma/M), folded per channel into
+//   dx = A1 * dy' + B1 * x + C1,   A1 = gamma*invstd, B1 = -A1*invstd*dgamma/M, C1 = -A1*dbeta/M - B1*mean
+// with the forward's own mask y = fma(x, scale, shift) <= 0.  Four rows in flight per thread.
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_apply_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, int lddy,
@@ -248,33 +274,57 @@ bn_bwd_apply_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, 
   const int rl = BN_THREADS / ct;
   const int col = threadIdx.x % ct, rlane = threadIdx.x / ct;
   const int c0 = (blockIdx.x * ct + col) * BN_VEC;
-  float mu[BN_VEC], is[BN_VEC], ga[BN_VEC], be[BN_VEC], k1[BN_VEC], k2[BN_VEC];
+  float A1[BN_VEC], B1[BN_VEC], C1[BN_VEC], sc[BN_VEC], sh[BN_VEC], cs[BN_VEC];
   const float invM = 1.f / (float)M;
 #pragma unroll
   for (int i = 0; i < BN_VEC; ++i) {
-    mu[i] = mean[c0 + i]; is[i] = invstd[c0 + i];
-    ga[i] = gamma ? gamma[c0 + i] : 1.f; be[i] = beta ? beta[c0 + i] : 0.f;
-    k1[i] = dbeta[c0 + i] * invM; k2[i] = dgamma[c0 + i] * invM;
+    const float mu = mean[c0 + i], is = invstd[c0 + i];
+    const float ga = gamma ? gamma[c0 + i] : 1.f, be = beta ? beta[c0 + i] : 0.f;
+    A1[i] = ga * is;
+    B1[i] = -A1[i] * is * (dgamma[c0 + i] * invM);
+    C1[i] = -A1[i] * (dbeta[c0 + i] * invM) - B1[i] * mu;
+    sc[i] = relu ? ga * is : 0.f;                 // same expressions as bn_finalize_fwd_kernel
+    sh[i] = relu ? be - mu * ga * is : 1.f;
+    cs[i] = 0.f;
   }
-  float cs[BN_VEC];
-#pragma unroll
-  for (int i = 0; i < BN_VEC; ++i) cs[i] = 0.f;
   const int rows_per = (M + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
-#pragma unroll 2
-  for (int r = r0 + rlane; r < r1; r += rl) {
+  int r = r0 + rlane;
+  for (; r + 3 * rl < r1; r += 4 * rl) {
+    float xv[4][BN_VEC], gv[4][BN_VEC];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      Vec8<T>::load(x + (size_t)(r + u * rl) * ldx + c0, xv[u]);
+      Vec8<T>::load(dy + (size_t)(r + u * rl) * lddy + c0, gv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < BN_VEC; ++i) {
+        const float g = fmaf(xv[u][i], sc[i], sh[i]) <= 0.f ? 0.f : gv[u][i];
+        xv[u][i] = fmaf(A1[i], g, fmaf(B1[i], xv[u][i], C1[i]));
+      }
+      Vec8<T>::store(dx + (size_t)(r + u * rl) * lddx + c0, xv[u]);
+      if (colsum_partial) {   // column sums of dx AS STORED (rounded to T): the bias gradient
+        float rv[BN_VEC];     // of the Linear in front of this BatchNorm (= sum_rows dY)
+        Vec8<T>::round(xv[u], rv);
+#pragma unroll
+        for (int i = 0; i < BN_VEC; ++i) cs[i] += rv[i];
+      }
+    }
+  }
+  for (; r < r1; r += rl) {
     float xv[BN_VEC], gv[BN_VEC];
     Vec8<T>::load(x + (size_t)r * ldx + c0, xv);
     Vec8<T>::load(dy + (size_t)r * lddy + c0, gv);
 #pragma unroll
     for (int i = 0; i < BN_VEC; ++i) {
-      const float xh = (xv[i] - mu[i]) * is[i];
-      const float g = (relu && fmaf(xh, ga[i], be[i]) <= 0.f) ? 0.f : gv[i];
-      xv[i] = ga[i] * is[i] * (g - k1[i] - xh * k2[i]);
+      const float g = fmaf(xv[i], sc[i], sh[i]) <= 0.f ? 0.f : gv[i];
+      xv[i] = fmaf(A1[i], g, fmaf(B1[i], xv[i], C1[i]));
     }
     Vec8<T>::store(dx + (size_t)r * lddx + c0, xv);
-    if (colsum_partial) {   // column sums of dx AS STORED (rounded to T): the bias gradient
-      float rv[BN_VEC];     // of the Linear in front of this BatchNorm (= sum_rows dY)
+    if (colsum_partial) {
+      float rv[BN_VEC];
       Vec8<T>::round(xv, rv);
 #pragma unroll
       for (int i = 0; i < BN_VEC; ++i) cs[i] += rv[i];
@@ -368,7 +418,8 @@ extern "C" int hsp_bn_relu_bwd(const void* x, int ldx, const void* dy, int lddy,
                                                             lddy, mean, invstd, gamma, beta, relu, M,
                                                             C, g.ct, part);
   HSP_LAUNCH_CHECK();
-  bn_finalize_bwd_kernel<<<(C + BN_FC - 1) / BN_FC, BN_FC * BN_FG, 0, st>>>(part, g.rchunks, C, dgamma, dbeta);
+  bn_finalize_bwd_kernel<<<(C + BN_FC - 1) / BN_FC, BN_FC * BN_FG, 0, st>>>(part, g.rchunks, C, mean, invstd,
+                                                                        dgamma, dbeta);
   HSP_LAUNCH_CHECK();
   if (dtype == HSP_DTYPE_BF16)
     bn_bwd_apply_kernel<__nv_bfloat16><<<grid, BN_THREADS, 0, st>>>(
@@ -382,7 +433,7 @@ extern "C" int hsp_bn_relu_bwd(const void* x, int ldx, const void* dy, int lddy,
   HSP_LAUNCH_CHECK();
   if (dx_colsum) {   // fixed-order sum of the per-CTA column sums (the second partial plane is zero)
     bn_finalize_bwd_kernel<<<(C + BN_FC - 1) / BN_FC, BN_FC * BN_FG, 0, st>>>(
-        part, g.rchunks, C, (float*)workspace + (size_t)g.rchunks * 2 * C, dx_colsum);
+        part, g.rchunks, C, nullptr, nullptr, (float*)workspace + (size_t)g.rchunks * 2 * C, dx_colsum);
     HSP_LAUNCH_CHECK();
   }
   return HSP_OK;
