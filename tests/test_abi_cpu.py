@@ -25,7 +25,7 @@ def _header_prototypes():
 def test_library_exports_every_header_symbol():
     from hspose_b200 import _lib
     protos = _header_prototypes()
-    assert len(protos) >= 25
+    assert len(protos) >= 27
     lib = ctypes.CDLL(_lib.LIB_PATH)          # loads on a GPU-less host
     for name in protos:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
@@ -47,7 +47,7 @@ def test_version_and_strerror_without_gpu():
     assert lib.hsp_version() >= 100
     assert b"argument" in lib.hsp_strerror(-1).lower() or lib.hsp_strerror(-1)
     # workspace queries are pure host arithmetic
-    assert lib.hsp_knn_feat_workspace_bytes(2, 1028) == 2 * 1028 * 4
+    assert lib.hsp_knn_feat_workspace_bytes(2, 1028) >= 2 * 1028 * 4   # row norms; more for the tensor-core path
     assert lib.hsp_bn_workspace_bytes(4112, 128) > 0
     assert lib.hsp_graph_conv_bwd_workspace_bytes(2, 1028, 20, 7, 128) > 0
 
