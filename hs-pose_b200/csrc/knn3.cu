@@ -200,6 +200,57 @@ knn3_reg_kernel(const float* __restrict__ query, const float* __restrict__ cand,
   }
 }
 
+// K = 1 (get_nearest_index, gcn3d.py:27-36; k = 1 queries in general): no selection network at all —
+// every lane keeps the smallest (distance, index) key of its candidates, one warp min-reduction.
+template <int FORMULA>
+__global__ void __launch_bounds__(KNN3_THREADS)
+knn3_nearest_kernel(const float* __restrict__ query, const float* __restrict__ cand, int M, int N,
+                    int qtile, int64_t* __restrict__ idx64, int32_t* __restrict__ idx32) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* s_c = reinterpret_cast<float4*>(smem_raw);
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* cb = cand + (size_t)b * N * 3;
+  for (int j = tid; j < N; j += KNN3_THREADS) {
+    float x = cb[3 * j], y = cb[3 * j + 1], z = cb[3 * j + 2];
+    s_c[j] = make_float4(x, y, z, sqnorm3(x, y, z));
+  }
+  __syncthreads();
+  const int q_end = min((int)(blockIdx.x + 1) * qtile, M);
+  for (int qi = blockIdx.x * qtile + warp; qi < q_end; qi += KNN3_WARPS) {
+    const float* qp = query + ((size_t)b * M + qi) * 3;
+    const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+    const float qq = sqnorm3(qx, qy, qz);
+    uint64_t best = KEY_MAX;
+#pragma unroll 4
+    for (int j = lane; j < N; j += 32)
+      best = umin64(best, make_key(dist3<FORMULA>(qx, qy, qz, qq, s_c[j]), (uint32_t)j));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) best = umin64(best, shfl_xor_u64(best, d));
+    if (lane == 0) {
+      const size_t o = (size_t)b * M + qi;
+      if (idx64) idx64[o] = (int64_t)(best & 0xffffffffu);
+      if (idx32) idx32[o] = (int32_t)(best & 0xffffffffu);
+    }
+  }
+}
+
+template <int FORMULA>
+static int launch_knn3_nearest(const float* query, const float* cand, int B, int M, int N,
+                               int64_t* idx64, int32_t* idx32, cudaStream_t st) {
+  size_t smem = (size_t)N * sizeof(float4);
+  auto kern = knn3_nearest_kernel<FORMULA>;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return HSP_ELAUNCH;
+  int qtile = 128;
+  while (qtile > KNN3_WARPS && (long)B * ((M + qtile - 1) / qtile) < 148L * 8) qtile >>= 1;
+  dim3 grid((M + qtile - 1) / qtile, B);
+  kern<<<grid, KNN3_THREADS, smem, st>>>(query, cand, M, N, qtile, idx64, idx32);
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}
+
 template <int NL, int FORMULA, int RPL>
 static int launch_knn3_reg(const float* query, const float* cand, int B, int M, int N, int K,
                            int drop, int64_t* idx64, int32_t* idx32, cudaStream_t st) {
@@ -263,6 +314,11 @@ extern "C" int hsp_knn3(const float* query, const float* cand, int B, int M, int
   if (B == 0 || M == 0) return HSP_OK;
   if (B > 65535) return HSP_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  if (K == 1) {
+    if (formula == HSP_DIST_NEIGHBOR)
+      return launch_knn3_nearest<HSP_DIST_NEIGHBOR>(query, cand, B, M, N, idx64, idx32, st);
+    return launch_knn3_nearest<HSP_DIST_NEAREST>(query, cand, B, M, N, idx64, idx32, st);
+  }
   if (K <= 32) {
     if (formula == HSP_DIST_NEIGHBOR)
       return dispatch_knn3_reg<1, HSP_DIST_NEIGHBOR>(query, cand, B, M, N, K, drop_first, idx64, idx32, st);

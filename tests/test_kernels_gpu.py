@@ -432,3 +432,32 @@ def test_residual_sum_fwd_bwd_vs_torch(cuda, ldt, sdt):
     assert torch.equal(lin.grad, go.to(ldt)) and torch.equal(ste.grad, go.to(sdt))
     out2 = ops.residual_sum(feat.detach(), None, None, ste.detach())     # optional terms
     assert torch.allclose(out2, feat.detach() + ste.detach().float(), atol=1e-6)
+
+
+def test_knn_feat_tensor_core_path_with_duplicate_rows(cuda):
+    """K2-TC under massive exact ties: 300 unique feature rows tiled to 1028 (what a mask with fewer than
+    1028 pixels produces, datasets/load_data.py:315-316).  Tied distances are ordered by index in both the
+    kernel and the oracle, the survivor lists overflow and the exact-scan fallback must take over."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(21)
+    base = torch.relu(torch.randn(2, 300, 128, generator=g) + 0.5)
+    rep = torch.cat([base, base, base, base[:, :128]], dim=1).contiguous()      # (2, 1028, 128)
+    got = ops.knn_feat(rep.to(cuda), 20, want64=True)[0].cpu().numpy()
+    assert np.array_equal(got, co.neighbor_index(rep.numpy(), 20))
+    # 90 identical rows: every distance ties
+    same = base[:, :1].expand(-1, 90, -1).contiguous()
+    got = ops.knn_feat(same.to(cuda), 8, want64=True)[0].cpu().numpy()
+    assert np.array_equal(got, co.neighbor_index(same.numpy(), 8))
+
+
+def test_knn3_k1_fast_path_vs_oracle(cuda):
+    """K = 1 (nearest, no drop) runs the min-reduction kernel: both distance formulas."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(8)
+    t = torch.randn(3, 500, 3, generator=g) * 0.05
+    s = t[:, torch.randperm(500, generator=g)[:77]].contiguous()
+    got = ops.knn3(t.to(cuda), s.to(cuda), 1, drop_first=0, formula=ops.DIST_NEAREST, want64=True)[0]
+    assert np.array_equal(got.cpu().numpy(), co.nearest_index(t.numpy(), s.numpy()))
+    got2 = ops.knn3(t.to(cuda), t.to(cuda), 1, drop_first=0, formula=ops.DIST_NEIGHBOR, want64=True)[0]
+    d = to.pairwise_neighbor_dist(t)
+    assert np.array_equal(got2.cpu().numpy()[..., 0], d.argmin(dim=-1).numpy())   # continuous data: no ties
