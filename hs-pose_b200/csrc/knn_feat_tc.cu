@@ -35,7 +35,6 @@ constexpr int QROWS = 128;                  // query rows per CTA = UMMA M
 constexpr int ROUND_COLS = 512;             // TMEM columns = candidates resident per round
 constexpr int LCAP = 92;                    // survivor list capacity per row (shared memory, 8 B entries)
 constexpr int SLOTS = 64;                   // running slot minima per row (slot = column mod 64)
-constexpr int SCAP = 96;                    // survivors per row handed to the refine kernel
 constexpr int SPITCH = DK + 4;              // staged candidate row pitch (floats): conflict-free LDS.128
 constexpr int THREADS = 128;
 // |d~ - d_fp32| <= EPS_REL * |f_i| * |f_j|.  Budget (units of |f_i||f_j|, x2 for the -2*inner factor):
@@ -242,7 +241,7 @@ __device__ __forceinline__ float exact_dist(const float* __restrict__ fi, const 
 __global__ void __launch_bounds__(THREADS, 1)
 knn_feat_tc_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* __restrict__ glo,
                    const float* __restrict__ qn, const float* __restrict__ qmax, int N, int T64, int K,
-                   uint16_t* __restrict__ surv_idx, int* __restrict__ surv_cnt) {
+                   uint2* __restrict__ surv, int* __restrict__ surv_cnt) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sA_hi = smem;                                   // [KC][128][8] bf16   32 KB
   unsigned char* sA_lo = sA_hi + 2 * TILE_BYTES;                 //                      32 KB
@@ -413,29 +412,27 @@ knn_feat_tc_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* _
     __syncthreads();                                  // TMEM / s_qn free for the next round
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
-  // final threshold is the tightest: drop survivors of earlier rounds that no longer qualify, and
-  // compact the indices to 16 bits in place (entry w is written after entry e >= w was read)
+  // final threshold is the tightest: drop survivors of earlier rounds that no longer qualify
   {
     const float lim = thr + eps2;
     uint2* my_list = s_list + tid * LCAP;
-    uint16_t* my_idx = reinterpret_cast<uint16_t*>(my_list);
     int w = 0;
     for (int e = 0; e < cnt; ++e) {
       const uint2 ev = my_list[e];
-      if (!(__uint_as_float(ev.x) > lim)) { my_idx[w] = (uint16_t)ev.y; ++w; }
+      if (!(__uint_as_float(ev.x) > lim)) { my_list[w] = ev; ++w; }
     }
     cnt = w;
   }
-  if (overflow || cnt > SCAP) cnt = -1;              // refine scans every candidate for this row
+  if (overflow) cnt = -1;                            // refine scans every candidate for this row
   __syncthreads();
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   if (row_ok) {
     surv_cnt[(size_t)b * N + i_row] = cnt;
-    const uint4* src = reinterpret_cast<const uint4*>(s_list + tid * LCAP);   // 16-bit indices, compacted above
-    uint4* dst = reinterpret_cast<uint4*>(surv_idx + ((size_t)b * N + i_row) * SCAP);
-#pragma unroll
-    for (int e = 0; e < SCAP * 2 / 16; ++e) dst[e] = src[e];
+    const uint4* src = reinterpret_cast<const uint4*>(s_list + tid * LCAP);
+    uint4* dst = reinterpret_cast<uint4*>(surv + ((size_t)b * N + i_row) * LCAP);
+    const int nv = cnt > 0 ? (cnt + 1) / 2 : 0;      // (approximate distance, index) pairs, 16 bytes = 2 entries
+    for (int e = 0; e < nv; ++e) dst[e] = src[e];
   }
 }
 
@@ -446,13 +443,19 @@ knn_feat_tc_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* _
 constexpr int RF_WARPS = 8;
 constexpr int RF_Q = 32;                    // features staged per pass (a quarter row)
 constexpr int RF_PITCH = RF_Q + 4;
+
+__device__ __forceinline__ float orderable_to_float(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
+
 template <int NL>
 __global__ void __launch_bounds__(RF_WARPS * 32)
-kf_refine_kernel(const float* __restrict__ feat, const float* __restrict__ qn, const uint16_t* __restrict__ surv_idx,
-                 const int* __restrict__ surv_cnt, int N, int rows_pad, int K, int drop,
-                 int64_t* __restrict__ idx64, int32_t* __restrict__ idx32) {
+kf_refine_kernel(const float* __restrict__ feat, const float* __restrict__ qn, const float* __restrict__ qmax,
+                 const uint2* __restrict__ surv, const int* __restrict__ surv_cnt, int N, int rows_pad, int K,
+                 int drop, int64_t* __restrict__ idx64, int32_t* __restrict__ idx32) {
   __shared__ __align__(16) float s_stage[RF_WARPS][32 * RF_PITCH];
   __shared__ uint64_t s_queue[RF_WARPS * 64];
+  __shared__ uint16_t s_sel[RF_WARPS][LCAP + 4];
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * RF_WARPS + warp;
   if (i >= N) return;
@@ -461,15 +464,42 @@ kf_refine_kernel(const float* __restrict__ feat, const float* __restrict__ qn, c
   const float4* a4 = reinterpret_cast<const float4*>(fb + (size_t)i * DK);
   const float q_i = qb[i];
   float* stage = s_stage[warp];
+  uint16_t* sel = s_sel[warp];
   const int c_r = surv_cnt[(size_t)b * N + i];
-  const uint16_t* li = surv_idx + ((size_t)b * N + i) * SCAP;
-  const int total = c_r >= 0 ? c_r : N;
+  int total = N;
+  if (c_r >= 0) {
+    // The filter's threshold was the K-th smallest of 64 slot minima (~26th smallest distance).  Here
+    // the K-th smallest approximate distance among (up to 64 of) the survivors themselves is a tighter,
+    // still valid upper bound: only survivors within 2*eps of it can be in the exact top-K.
+    const uint2* li = surv + ((size_t)b * N + i) * LCAP;
+    uint2 e[3];
+    uint32_t o[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      e[u] = make_uint2(0x7f800000u, 0u);
+      if (lane + 32 * u < c_r) e[u] = __ldg(li + lane + 32 * u);
+      o[u] = (lane + 32 * u < c_r) ? float_orderable(__uint_as_float(e[u].x)) : 0xffffffffu;
+    }
+    const uint32_t tau_o = warp_kth_smallest64(o[0], o[1], K, lane);
+    const float eps2 = 2.0f * EPS_REL * sqrtf(fmaxf(q_i, 0.0f) * __ldg(qmax + b)) + 1e-30f;
+    const float lim = orderable_to_float(tau_o) + eps2;
+    int w = 0;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const bool keep = (lane + 32 * u < c_r) && !(__uint_as_float(e[u].x) > lim);
+      const unsigned mk = __ballot_sync(0xffffffffu, keep);
+      if (keep) sel[w + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)e[u].y;
+      w += __popc(mk);
+    }
+    total = w;
+    __syncwarp();
+  }
   const int sub = lane >> 3, l8 = lane & 7;           // 4 rows per fetch instruction, 8 lanes x 16 B each
   WarpTopK<NL> top;
   top.reset(s_queue + warp * 64);
   for (int base = 0; base < total; base += 32) {
     const int nb = min(32, total - base);
-    int jl = lane < nb ? (c_r >= 0 ? (int)li[base + lane] : base + lane) : 0;
+    int jl = lane < nb ? (c_r >= 0 ? (int)sel[base + lane] : base + lane) : 0;
     jl = min(jl, N - 1);
     float acc = 0.0f;
     for (int qd = 0; qd < DK; qd += RF_Q) {
@@ -525,7 +555,7 @@ static int kf_tc_tiles(int N) { return 2 * ((N + 127) / 128); }
 size_t knn_feat_tc_workspace_bytes(int B, int N) {
   const size_t T64 = kf_tc_tiles(N);
   return (size_t)B * T64 * tc::TILE_BYTES * 2 + (size_t)B * T64 * tc::TR * sizeof(float) + (size_t)B * sizeof(float) +
-         (size_t)B * N * (tc::SCAP * sizeof(uint16_t) + sizeof(int)) + 1024;
+         (size_t)B * N * (tc::LCAP * sizeof(uint2) + sizeof(int)) + 1024;
 }
 
 // D = 128, K = k + drop <= 64, N <= 65535.
@@ -540,8 +570,8 @@ int knn_feat_tc_launch(const float* feat, int B, int N, int K, int drop, int64_t
   float* qn = (float*)(ws + (size_t)B * T64 * TILE_BYTES * 2);
   float* qmax = qn + (size_t)B * T64 * TR;
   uintptr_t p = ((uintptr_t)(qmax + B) + 127) & ~(uintptr_t)127;
-  uint16_t* surv_idx = (uint16_t*)p;
-  int* surv_cnt = (int*)(p + (size_t)B * N * SCAP * sizeof(uint16_t));
+  uint2* surv = (uint2*)p;
+  int* surv_cnt = (int*)(p + (size_t)B * N * LCAP * sizeof(uint2));
   if (cudaMemsetAsync(qmax, 0, sizeof(float) * B, st) != cudaSuccess) return HSP_ELAUNCH;
   kf_norm_kernel<<<dim3((T64 * TR + 127) / 128, B), 128, 0, st>>>(feat, N, T64 * TR, qn, qmax);
   HSP_LAUNCH_CHECK();
@@ -551,14 +581,14 @@ int knn_feat_tc_launch(const float* feat, int B, int N, int K, int drop, int64_t
   if (cudaFuncSetAttribute(knn_feat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
       cudaSuccess)
     return HSP_ELAUNCH;
-  knn_feat_tc_kernel<<<dim3(T64 / 2, B), THREADS, smem, st>>>(hi, lo, qn, qmax, N, T64, K, surv_idx, surv_cnt);
+  knn_feat_tc_kernel<<<dim3(T64 / 2, B), THREADS, smem, st>>>(hi, lo, qn, qmax, N, T64, K, surv, surv_cnt);
   HSP_LAUNCH_CHECK();
   if (K <= 32)
     kf_refine_kernel<1><<<dim3((N + RF_WARPS - 1) / RF_WARPS, B), RF_WARPS * 32, 0, st>>>(
-        feat, qn, surv_idx, surv_cnt, N, T64 * TR, K, drop, idx64, idx32);
+        feat, qn, qmax, surv, surv_cnt, N, T64 * TR, K, drop, idx64, idx32);
   else
     kf_refine_kernel<2><<<dim3((N + RF_WARPS - 1) / RF_WARPS, B), RF_WARPS * 32, 0, st>>>(
-        feat, qn, surv_idx, surv_cnt, N, T64 * TR, K, drop, idx64, idx32);
+        feat, qn, qmax, surv, surv_cnt, N, T64 * TR, K, drop, idx64, idx32);
   HSP_LAUNCH_CHECK();
   return HSP_OK;
 }
