@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .FaceRecon import conv_bn_relu_points
 from .flags import FLAGS
 
@@ -32,7 +33,10 @@ class _PointHead(nn.Module):
         # `first` is relu(bn1(conv1(x))) when PoseNet9D already computed it jointly with the others
         x = first if first is not None else conv_bn_relu_points(self.conv1, self.bn1, x_bnc)
         x = conv_bn_relu_points(self.conv2, self.bn2, x)
-        x = torch.max(x, 1)[0]                                  # (bs, 256): max over points
+        if x.is_cuda and x.shape[-1] % 8 == 0 and x.dtype in (torch.float32, torch.bfloat16):
+            x = ops.colmax(x)                                   # (bs, 256): max over points
+        else:
+            x = torch.max(x, 1)[0]
         x = F.relu(self.bn3(F.linear(x, self.conv3.weight[:, :, 0], self.conv3.bias)))
         x = self.drop1(x)
         x = F.linear(x, self.conv4.weight[:, :, 0], self.conv4.bias)

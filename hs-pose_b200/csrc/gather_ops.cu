@@ -282,6 +282,49 @@ static bool vec8_ok(const void* a, const void* b, int C, int ldo, int col0, int 
          ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0;
 }
 
+// Max over the points of one object (the `torch.max(x, 2)` that feeds the last block of every pose
+// head, reference PoseR.py:30 / PoseTs.py:35) on a (B, N, C) bf16 / fp32 activation: CTA = (object,
+// 64-channel slab), thread = 8 channels x a row lane, 16-byte loads, fixed-order combine in shared
+// memory (ties -> lowest row, deterministic).  out (B, C) same dtype as x, arg (B, C) int32.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colmax_kernel(const T* __restrict__ x, int N, int C, T* __restrict__ out, int32_t* __restrict__ arg) {
+  __shared__ float s_v[32][64];
+  __shared__ int s_i[32][64];
+  const int b = blockIdx.y, cv = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + cv * 8;
+  float m[8];
+  int am[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { m[i] = -INFINITY; am[i] = 0; }
+  if (c0 < C) {
+    const T* xb = x + (size_t)b * N * C + c0;
+#pragma unroll 2
+    for (int r = rl; r < N; r += 32) {
+      float4 a, c;
+      Out8<T>::load(xb + (size_t)r * C, a, c);
+      const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (v[i] > m[i]) { m[i] = v[i]; am[i] = r; }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s_v[rl][cv * 8 + i] = m[i]; s_i[rl][cv * 8 + i] = am[i]; }
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < C) {
+    float best = s_v[0][threadIdx.x];
+    int bi = s_i[0][threadIdx.x];
+    for (int l = 1; l < 32; ++l) {
+      const float v = s_v[l][threadIdx.x];
+      const int vi = s_i[l][threadIdx.x];
+      if (v > best || (v == best && vi < bi)) { best = v; bi = vi; }
+    }
+    out[(size_t)b * C + blockIdx.x * 64 + threadIdx.x] = from_f32<T>(best);
+    arg[(size_t)b * C + blockIdx.x * 64 + threadIdx.x] = bi;
+  }
+}
+
 static int orl_tile(int N) { return 16; }
 
 }  // namespace hsp
@@ -431,6 +474,24 @@ extern "C" int hsp_upsample_rows_bwd(const void* gout, const int32_t* nn, int B,
   else
     upsample_bwd_kernel<float><<<grid, GO_THREADS, 0, (cudaStream_t)stream>>>(
         (const float*)gout, nn, Nsrc, M, C, ldo, col0, gfeat);
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}
+
+extern "C" int hsp_colmax_fwd(const void* x, int dtype, int B, int N, int C, void* out, int32_t* arg,
+                              void* stream) {
+  using namespace hsp;
+  if (!x || !out || !arg || B < 0 || N <= 0 || C <= 0 || (C % 8) != 0 || B > 65535 ||
+      (((uintptr_t)x) & 15) != 0)
+    return HSP_EINVAL;
+  if (dtype != HSP_DTYPE_F32 && dtype != HSP_DTYPE_BF16) return HSP_EINVAL;
+  if (B == 0) return HSP_OK;
+  dim3 grid((C + 63) / 64, B);
+  if (dtype == HSP_DTYPE_BF16)
+    colmax_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, N, C, (__nv_bfloat16*)out, arg);
+  else
+    colmax_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, N, C, (float*)out, arg);
   HSP_LAUNCH_CHECK();
   return HSP_OK;
 }

@@ -19,7 +19,9 @@ class TrainStep:
                  tf32=True):
         self.model, self.clip, self.amp, self.use_graph = model, clip, amp, graph
         self.flat = parallel.FlatGradients(model.posenet.parameters())
-        self.opt = optimizer or torch.optim.Adam(self.flat.params, lr=lr, fused=True, capturable=graph)
+        # default optimiser: Adam over ONE flat parameter (see FlatGradients.flatten_params)
+        self.opt = optimizer or torch.optim.Adam([self.flat.flatten_params()], lr=lr, fused=True,
+                                                 capturable=graph)
         self.graph = None
         self.static_batch = None
         self.static_loss = None

@@ -502,6 +502,38 @@ def residual_sum(feature, lin=None, gproj=None, ste=None):
     return _ResidualSum.apply(feature, lin, gproj, ste)
 
 
+class _ColMax(torch.autograd.Function):
+    """out[b,c] = max_i x[b,i,c] on a point-major (B,N,C) activation (fp32 / bf16)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        if not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
+            raise _lib.HSPoseLibraryError("colmax: expected a CUDA fp32/bf16 (B,N,C) tensor")
+        x = x if x.is_contiguous() else x.contiguous()
+        B, N, C = x.shape
+        with torch.cuda.device(x.device):
+            out = torch.empty(B, C, dtype=x.dtype, device=x.device)
+            arg = torch.empty(B, C, dtype=torch.int32, device=x.device)
+            _call("hsp_colmax_fwd", _p(x), BF16 if x.dtype == torch.bfloat16 else F32, B, N, C, _p(out),
+                  _p(arg), _stream())
+        ctx.save_for_backward(arg)
+        ctx.meta = (B, N, C, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        B, N, C, dt = ctx.meta
+        gx = torch.zeros(B, N, C, dtype=dt, device=g.device)
+        gx.scatter_(1, arg.long().unsqueeze(1), g.to(dt).unsqueeze(1))
+        return gx
+
+
+def colmax(x):
+    """Max over the points (dim 1) of a (B,N,C) activation."""
+    return _ColMax.apply(x)
+
+
 # ------------------------------------------------------------ BatchNorm + ReLU
 class _BnRelu(torch.autograd.Function):
     """Batch-statistics BatchNorm1d (+ReLU) on a (M,C) matrix (K6b); x may be a column

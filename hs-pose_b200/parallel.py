@@ -69,6 +69,26 @@ class FlatGradients:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.flat_param = None
+
+    def flatten_params(self):
+        """Re-home every parameter's storage as a view of ONE flat buffer (same order as the flat
+        gradient) and return it as a single nn.Parameter whose .grad is the flat gradient: the
+        optimiser step then is one element-wise kernel over 9.7 M elements instead of one
+        multi-tensor launch group per 160 tensors.  Module parameters keep their identity, names and
+        values (state_dict is unchanged); only their storage moves."""
+        if self.flat_param is None:
+            flat = torch.empty_like(self.flat)
+            off = 0
+            with torch.no_grad():
+                for p in self.params:
+                    n = p.numel()
+                    flat[off:off + n].copy_(p.reshape(-1))
+                    p.data = flat[off:off + n].view_as(p)
+                    off += n
+            self.flat_param = torch.nn.Parameter(flat)
+            self.flat_param.grad = self.flat
+        return self.flat_param
 
     def zero(self):
         """zero_grad() that keeps the views (never set_to_none)."""

@@ -182,6 +182,13 @@ int hsp_residual_sum_fwd(const float* feature, const void* lin, int lin_dtype,
 int hsp_residual_sum_bwd(const float* g, int B, int N, int C, void* g_bf16, float* g_gproj,
                          void* stream);
 
+/* Max over the points of every object (the torch.max(x, 2) in front of the last
+ * block of each pose head, PoseR.py:30, PoseTs.py:35) on a (B,N,C) activation in
+ * point-major layout: out (B,C) (same dtype as x, HSP_DTYPE_*), arg (B,C) int32 =
+ * the winning point (ties -> lowest index).  C % 8 == 0.                      */
+int hsp_colmax_fwd(const void* x, int dtype, int B, int N, int C, void* out, int32_t* arg,
+                   void* stream);
+
 /* ------------------------------------------------------------------ K7 ---
  * Chamfer distance (tools/pyTorchChamferDistance/chamfer_distance.cu:6-187):
  * for each point of a (B,N,3) the squared distance to / index of the nearest

@@ -461,3 +461,21 @@ def test_knn3_k1_fast_path_vs_oracle(cuda):
     got2 = ops.knn3(t.to(cuda), t.to(cuda), 1, drop_first=0, formula=ops.DIST_NEIGHBOR, want64=True)[0]
     d = to.pairwise_neighbor_dist(t)
     assert np.array_equal(got2.cpu().numpy()[..., 0], d.argmin(dim=-1).numpy())   # continuous data: no ties
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_colmax_fwd_bwd_vs_torch(cuda, dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    x = torch.relu(torch.randn(5, 1028, 256, generator=g)).to(cuda).to(dtype).requires_grad_()
+    out = ops.colmax(x)
+    ref, idx = x.detach().max(dim=1)
+    assert torch.equal(out, ref)
+    go = torch.randn(5, 256, generator=g).to(cuda).to(dtype)
+    out.backward(go)
+    # gradient lands on one maximal point per (object, channel); where the max is unique it is torch's
+    gsum = x.grad.float().sum(dim=1)
+    assert torch.allclose(gsum, go.float(), atol=1e-3)
+    assert ((x.grad != 0).sum(dim=1) <= 1).all()
+    picked = x.detach().gather(1, x.grad.ne(0).float().argmax(dim=1, keepdim=True)).squeeze(1)
+    assert torch.equal(torch.where(go != 0, picked, ref), ref)

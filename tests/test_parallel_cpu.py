@@ -79,3 +79,30 @@ def test_clip_matches_torch():
     assert torch.allclose(n1, tot)
     for p, r in zip(net.parameters(), ref):
         assert torch.allclose(p.grad, r * min(1.0, 0.5 / (tot.item() + 1e-6)), atol=1e-6)
+
+
+def test_flat_parameter_adam_equals_per_tensor_adam():
+    """FlatGradients.flatten_params: parameters become views of one flat buffer (values, names and
+    state_dict unchanged) and Adam over that single flat parameter takes exactly the per-tensor step."""
+    import copy
+    from hspose_b200 import parallel
+    torch.manual_seed(0)
+    net_a = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 3))
+    net_b = copy.deepcopy(net_a)
+    sd0 = {k: v.clone() for k, v in net_b.state_dict().items()}
+    flat = parallel.FlatGradients(net_b.parameters())
+    fp = flat.flatten_params()
+    for k, v in net_b.state_dict().items():
+        assert torch.equal(v, sd0[k]), k
+    opt_a = torch.optim.Adam(net_a.parameters(), lr=1e-2)
+    opt_b = torch.optim.Adam([fp], lr=1e-2)
+    x = torch.randn(16, 7)
+    for _ in range(3):
+        opt_a.zero_grad()
+        net_a(x).square().mean().backward()
+        opt_a.step()
+        flat.zero()
+        net_b(x).square().mean().backward()
+        opt_b.step()
+    for (n, pa), (_, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
+        assert torch.allclose(pa, pb, atol=1e-7), n
