@@ -235,7 +235,7 @@ def peaks():
 def cpu_port_throughput(sample_objects, steps, warmup, seed=1):
     """The oracle port of the SAME train step on the host cores (all threads)."""
     import torch
-    from oracle.synth import synth_batch
+    from hspose_b200.synth import synth_batch
     from oracle.train_step import OracleTrainer
     from hspose_b200.HSPose import HSPose
     torch.set_num_threads(os.cpu_count() or 1)
@@ -282,7 +282,7 @@ def run_b200(args):
     from hspose_b200 import _lib, parallel
     from hspose_b200.engine import TrainStep
     from hspose_b200.HSPose import HSPose
-    from oracle.synth import synth_batch  # seeded synthetic inputs only (no oracle compute)
+    from hspose_b200.synth import synth_batch  # seeded synthetic inputs only (no oracle compute)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")

@@ -4,7 +4,7 @@ import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle.synth import fill_params, synth_batch
+from hspose_b200.synth import fill_params, synth_batch
 import hspose_b200.flags as hf
 from hspose_b200 import gcn3d
 from hspose_b200.HSPose import HSPose

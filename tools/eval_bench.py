@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hspose_b200.flags as hf  # noqa: E402
 from hspose_b200 import gcn3d  # noqa: E402
 from hspose_b200.PoseNet9D import PoseNet9D  # noqa: E402
-from oracle.synth import fill_params, synth_batch  # noqa: E402
+from hspose_b200.synth import fill_params, synth_batch  # noqa: E402
 
 dev = torch.device("cuda:0")
 torch.backends.cuda.matmul.allow_tf32 = False

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from hspose_b200 import parallel  # noqa: E402
 from hspose_b200.HSPose import HSPose  # noqa: E402
-from oracle.synth import synth_batch  # noqa: E402
+from hspose_b200.synth import synth_batch  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 amp = (sys.argv[2] if len(sys.argv) > 2 else "bf16") == "bf16"

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from hspose_b200.engine import TrainStep
 from hspose_b200.HSPose import HSPose
-from oracle.synth import synth_batch
+from hspose_b200.synth import synth_batch
 from torch.profiler import ProfilerActivity, profile
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 dev = torch.device("cuda:0")

@@ -3,7 +3,7 @@ sys.path.insert(0, "/root/repo")
 import hspose_b200.ops as ops
 from hspose_b200 import _lib, gcn3d
 from hspose_b200.HSPose import HSPose
-from oracle.synth import synth_batch
+from hspose_b200.synth import synth_batch
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 B = 16
