@@ -479,3 +479,22 @@ def test_colmax_fwd_bwd_vs_torch(cuda, dtype):
     assert ((x.grad != 0).sum(dim=1) <= 1).all()
     picked = x.detach().gather(1, x.grad.ne(0).float().argmax(dim=1, keepdim=True)).squeeze(1)
     assert torch.equal(torch.where(go != 0, picked, ref), ref)
+
+
+@pytest.mark.parametrize("N", [21, 40, 64, 65, 127, 129, 300, 513, 700, 1100])
+def test_knn_ragged_sizes_vs_oracle(cuda, N):
+    """Ragged sizes around every tile boundary of K1 (32-candidate register blocks, 1056-candidate blocks)
+    and K2 / K2-TC (64-row tiles, 128-row query blocks, 512-column TMEM rounds), k from 1 to N-1-ish."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(1000 + N)
+    B = 2
+    xyz = torch.randn(B, N, 3, generator=g) * 0.05
+    f128 = torch.relu(torch.randn(B, N, 128, generator=g) + 0.3)
+    f64 = torch.relu(torch.randn(B, N, 64, generator=g) + 0.3)
+    for k in sorted({1, 8, min(20, N - 1), min(40, N - 1)}):
+        got = ops.knn3(xyz.to(cuda), xyz.to(cuda), k, want64=True)[0].cpu().numpy()
+        assert np.array_equal(got, co.neighbor_index(xyz.numpy(), k)), ("knn3", N, k)
+        got = ops.knn_feat(f128.to(cuda), k, want64=True)[0].cpu().numpy()       # tensor-core filter path
+        assert np.array_equal(got, co.neighbor_index(f128.numpy(), k)), ("knn_feat128", N, k)
+        got = ops.knn_feat(f64.to(cuda), k, want64=True)[0].cpu().numpy()        # all-FP32 FFMA2 path
+        assert np.array_equal(got, co.neighbor_index(f64.numpy(), k)), ("knn_feat64", N, k)
