@@ -249,15 +249,13 @@ class _HSConvMixed(torch.autograd.Function):
         B, N, Cin = fm.shape
         gout = _need(gout.float(), torch.float32, "gout")
         gP, gdirn, gb = _graph_conv_bwd_raw(xyz, idx32, dirn, P, am, gout, S, C, want_gbias=True)
-        gP2 = gP.view(B * N, (S + 1) * C)
+        # weight / input gradients as bf16 tensor-core GEMMs (fp32 accumulate): one cast pass over gP,
+        # then both GEMMs read half the bytes and run on the tcgen05 library kernels
+        gP16 = gP.view(B * N, (S + 1) * C).to(torch.bfloat16)
         with torch.autocast("cuda", enabled=False):
-            prev = torch.backends.cuda.matmul.allow_tf32
-            torch.backends.cuda.matmul.allow_tf32 = True
-            try:
-                gfm = (gP2 @ W.t()).view(B, N, Cin) if ctx.needs_input_grad[3] else None
-                gW = fm.reshape(B * N, Cin).t() @ gP2
-            finally:
-                torch.backends.cuda.matmul.allow_tf32 = prev
+            W16 = W.to(torch.bfloat16)
+            gfm = (gP16 @ W16.t()).view(B, N, Cin).float() if ctx.needs_input_grad[3] else None
+            gW = (fm.reshape(B * N, Cin).to(torch.bfloat16).t() @ gP16).float()
         return None, None, gdirn, gfm, gW, gb, None, None
 
 
