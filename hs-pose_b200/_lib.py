@@ -37,8 +37,8 @@ SIGNATURES = {
                                 c_int, P, P, P, P, P, P, c_int, P, c_size_t, P]),
     "hsp_bn_relu_bwd": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, P, P, P, P, c_int, P, P, P,
                                 c_int, P, P, c_size_t, P]),
-    "hsp_residual_sum_fwd": (c_int, [P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P]),
-    "hsp_residual_sum_bwd": (c_int, [P, c_int, c_int, c_int, P, P, P]),
+    "hsp_residual_sum_fwd": (c_int, [P, P, c_int, P, P, c_int, P, P, c_int, c_int, c_int, P, P]),
+    "hsp_residual_sum_bwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P]),
     "hsp_colmax_fwd": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P]),
     "hsp_chamfer_fwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P, P]),
     "hsp_chamfer_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, P]),

@@ -144,7 +144,7 @@ def get_ORL_global(feature, vertices, neighbor_num):
     return G.unsqueeze(1).repeat(1, feature.size(1), 1)
 
 
-def _orl_fuse(feature, vertices, neighbor_num, conv2_weight, f_STE=None):
+def _orl_fuse(feature, vertices, neighbor_num, conv2_weight, f_STE=None, ste_xyz_weight=None):
     """ORL_forward (gcn3d.py:109-113 / :183-187) without the cat/repeat:
     conv2(cat[f, G]) = f @ W2[:, :C]^T + (G @ W2[:, C:]^T) broadcast over points, and the
     layer's `+ f_STE` (gcn3d.py:90 / :156) folded into the same pass (K5d) when given."""
@@ -155,7 +155,12 @@ def _orl_fuse(feature, vertices, neighbor_num, conv2_weight, f_STE=None):
     with torch.autocast("cuda", enabled=False):
         gproj = F.linear(G.float(), W2[:, C:].float())                       # (B,C), tiny: keep fp32
     if C % 4 == 0 and feature.dtype == torch.float32:
+        if ste_xyz_weight is not None:   # surface layer: STE = 3 -> C linear on xyz, evaluated in the same pass
+            return ops.residual_sum(feature, lin, gproj, None, vertices.float(), ste_xyz_weight.float())
         return ops.residual_sum(feature, lin, gproj, f_STE)
+    if ste_xyz_weight is not None:
+        with torch.autocast("cuda", enabled=False):
+            f_STE = F.linear(vertices.float(), ste_xyz_weight.float())
     out = feature + lin + gproj.unsqueeze(1)
     return out if f_STE is None else out + f_STE
 
@@ -181,10 +186,10 @@ class HSlayer_surface(nn.Module):
         self.directions.data.uniform_(-stdv, stdv)
 
     def forward(self, vertices: "(bs, vertice_num, 3)", neighbor_num: 'int'):
-        with torch.autocast("cuda", enabled=False):   # K = 3: keep the coordinates in fp32
-            f_STE = F.linear(vertices.float(), self.STE_layer.weight[:, :, 0])
+        # STE (Conv1d 3 -> C on the coordinates, gcn3d.py:86) is folded into the fused residual pass
         feature = self.graph_conv(None, vertices, neighbor_num)
-        return _orl_fuse(feature, vertices, neighbor_num, self.conv2.weight, f_STE)
+        return _orl_fuse(feature, vertices, neighbor_num, self.conv2.weight,
+                         ste_xyz_weight=self.STE_layer.weight[:, :, 0])
 
     def graph_conv(self, receptive_fields_norm, vertices, neighbor_num):
         """K3.  `receptive_fields_norm` is accepted for signature parity and ignored:

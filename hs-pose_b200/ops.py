@@ -450,11 +450,13 @@ def concat_upsample(pieces, nns, M, ld=None, out_dtype=torch.float32):
 
 
 class _ResidualSum(torch.autograd.Function):
-    """out = feature + lin + gproj[:, None, :] + ste in one pass (K5d); backward = one pass that
-    emits the bf16 cast of the gradient (for bf16 lin / ste) and the per-object column sums."""
+    """out = feature + lin + gproj[:, None, :] + ste in one pass (K5d); `ste` is either a (B,N,C)
+    tensor or, for the surface layer, the pair (xyz (B,N,3), wxyz (C,3)) evaluated in place.
+    Backward = one pass that emits the bf16 cast of the gradient (for bf16 lin / ste), the per-object
+    column sums and the per-object partials of d wxyz."""
 
     @staticmethod
-    def forward(ctx, feature, lin, gproj, ste):
+    def forward(ctx, feature, lin, gproj, ste, xyz, wxyz):
         feature = _need(feature, torch.float32, "feature")
         B, N, C = feature.shape
 
@@ -467,37 +469,48 @@ class _ResidualSum(torch.autograd.Function):
         lin, ldt = prep(lin, "lin")
         ste, sdt = prep(ste, "ste")
         gproj = _need(gproj, torch.float32, "gproj") if gproj is not None else None
+        if xyz is not None:
+            xyz = _need(xyz, torch.float32, "xyz")
+            wxyz = _need(wxyz, torch.float32, "wxyz")
+            if xyz.shape != (B, N, 3) or wxyz.shape != (C, 3) or ste is not None:
+                raise ValueError("residual_sum: xyz (B,N,3) + wxyz (C,3) replace ste")
         with torch.cuda.device(feature.device):
             out = torch.empty_like(feature)
-            _call("hsp_residual_sum_fwd", _p(feature), _p(lin), ldt, _p(gproj), _p(ste), sdt, B, N, C,
-                  _p(out), _stream())
+            _call("hsp_residual_sum_fwd", _p(feature), _p(lin), ldt, _p(gproj), _p(ste), sdt, _p(xyz),
+                  _p(wxyz), B, N, C, _p(out), _stream())
+        ctx.save_for_backward(xyz)
         ctx.meta = (B, N, C, None if lin is None else ldt, None if ste is None else sdt, gproj is not None)
         return out
 
     @staticmethod
     def backward(ctx, g):
         B, N, C, ldt, sdt, has_gp = ctx.meta
+        (xyz,) = ctx.saved_tensors
         g = _need(g.float(), torch.float32, "g")
         want16 = (ldt == BF16 and ctx.needs_input_grad[1]) or (sdt == BF16 and ctx.needs_input_grad[3])
         want_gp = has_gp and ctx.needs_input_grad[2]
-        g16 = ggp = None
-        if want16 or want_gp:
+        want_w = xyz is not None and ctx.needs_input_grad[5]
+        g16 = ggp = gwp = None
+        if want16 or want_gp or want_w:
             with torch.cuda.device(g.device):
                 g16 = torch.empty(B, N, C, dtype=torch.bfloat16, device=g.device) if want16 else None
                 ggp = torch.empty(B, C, dtype=torch.float32, device=g.device) if want_gp else None
-                _call("hsp_residual_sum_bwd", _p(g), B, N, C, _p(g16), _p(ggp), _stream())
+                gwp = torch.empty(B, C, 3, dtype=torch.float32, device=g.device) if want_w else None
+                _call("hsp_residual_sum_bwd", _p(g), _p(xyz) if want_w else None, B, N, C, _p(g16), _p(ggp),
+                      _p(gwp), _stream())
 
         def pick(dt, need):
             if dt is None or not need:
                 return None
             return g16 if dt == BF16 else g
         return (g if ctx.needs_input_grad[0] else None, pick(ldt, ctx.needs_input_grad[1]), ggp,
-                pick(sdt, ctx.needs_input_grad[3]))
+                pick(sdt, ctx.needs_input_grad[3]), None, gwp.sum(dim=0) if want_w else None)
 
 
-def residual_sum(feature, lin=None, gproj=None, ste=None):
-    """K5d: feature + lin + gproj[:, None, :] + ste  ((B,N,C); gproj (B,C))."""
-    return _ResidualSum.apply(feature, lin, gproj, ste)
+def residual_sum(feature, lin=None, gproj=None, ste=None, xyz=None, wxyz=None):
+    """K5d: feature + lin + gproj[:, None, :] + ste  ((B,N,C); gproj (B,C)); ste may be given as
+    xyz (B,N,3) + wxyz (C,3) (the surface layer's coordinate STE)."""
+    return _ResidualSum.apply(feature, lin, gproj, ste, xyz, wxyz)
 
 
 class _ColMax(torch.autograd.Function):

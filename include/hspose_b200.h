@@ -172,15 +172,20 @@ int hsp_upsample_rows_bwd(const void* gout, const int32_t* nn, int B, int Nsrc,
  *   out[b,i,c] = feature[b,i,c] + lin[b,i,c] + gproj[b,c] + ste[b,i,c]
  * lin = feature @ W2[:, :C]^T and ste = STE(layer input) are (B,N,C) fp32 or bf16
  * (HSP_DTYPE_*), gproj = G @ W2[:, C:]^T is (B,C) fp32; lin, gproj, ste may each
- * be NULL.  C % 4 == 0.
+ * be NULL.  The surface layer's STE is a 3 -> C linear on the coordinates
+ * (HSlayer_surface.STE_layer, gcn3d.py:71,86): pass xyz (B,N,3) and wxyz (C,3)
+ * instead of ste and it is evaluated in the same pass.  C % 4 == 0.
  * bwd: g = d out (B,N,C) fp32.  g_bf16 (B,N,C) bf16 (optional) = cast(g) — the
- * gradient of a bf16 lin / ste; g_gproj (B,C) (optional) = sum_i g[b,i,:].
- * d feature = g needs no kernel.                                            */
+ * gradient of a bf16 lin / ste; g_gproj (B,C) (optional) = sum_i g[b,i,:];
+ * g_wxyz_partial (B,C,3) (optional, needs xyz) = sum_i g[b,i,c]*xyz[b,i,d], the
+ * per-object part of d wxyz (the caller adds the B slices).  d feature = g
+ * needs no kernel.                                                          */
 int hsp_residual_sum_fwd(const float* feature, const void* lin, int lin_dtype,
-                         const float* gproj, const void* ste, int ste_dtype, int B, int N,
-                         int C, float* out, void* stream);
-int hsp_residual_sum_bwd(const float* g, int B, int N, int C, void* g_bf16, float* g_gproj,
-                         void* stream);
+                         const float* gproj, const void* ste, int ste_dtype,
+                         const float* xyz, const float* wxyz, int B, int N, int C,
+                         float* out, void* stream);
+int hsp_residual_sum_bwd(const float* g, const float* xyz, int B, int N, int C, void* g_bf16,
+                         float* g_gproj, float* g_wxyz_partial, void* stream);
 
 /* Max over the points of every object (the torch.max(x, 2) in front of the last
  * block of each pose head, PoseR.py:30, PoseTs.py:35) on a (B,N,C) activation in

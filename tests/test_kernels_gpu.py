@@ -498,3 +498,24 @@ def test_knn_ragged_sizes_vs_oracle(cuda, N):
         assert np.array_equal(got, co.neighbor_index(f128.numpy(), k)), ("knn_feat128", N, k)
         got = ops.knn_feat(f64.to(cuda), k, want64=True)[0].cpu().numpy()        # all-FP32 FFMA2 path
         assert np.array_equal(got, co.neighbor_index(f64.numpy(), k)), ("knn_feat64", N, k)
+
+
+def test_residual_sum_xyz_ste_mode(cuda):
+    """K5d with the surface layer's coordinate STE folded in: feature + lin + gproj + xyz @ W^T."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(6)
+    B, N, C = 3, 300, 128
+    feat = torch.randn(B, N, C, generator=g).to(cuda).requires_grad_()
+    lin = torch.randn(B, N, C, generator=g).to(cuda).to(torch.bfloat16).requires_grad_()
+    gp = torch.randn(B, C, generator=g).to(cuda).requires_grad_()
+    xyz = (torch.randn(B, N, 3, generator=g) * 0.05).to(cuda)
+    W = torch.randn(C, 3, generator=g).to(cuda).requires_grad_()
+    go = torch.randn(B, N, C, generator=g).to(cuda)
+    out = ops.residual_sum(feat, lin, gp, None, xyz, W)
+    out.backward(go)
+    Wr = W.detach().clone().requires_grad_()
+    ref = feat.detach() + lin.detach().float() + gp.detach()[:, None, :] + xyz @ Wr.t()
+    ref.backward(go)
+    assert torch.allclose(out, ref, atol=1e-6)
+    assert torch.allclose(W.grad, Wr.grad, atol=1e-4, rtol=1e-5)
+    assert torch.equal(feat.grad, go) and torch.allclose(gp.grad, go.sum(1), atol=1e-4)
