@@ -265,8 +265,9 @@ static int launch_knn_feat(const float* feat, const float* qn, int B, int N, int
 
 namespace hsp {
 size_t knn_feat_tc_workspace_bytes(int B, int N);
-int knn_feat_tc_launch(const float* feat, int B, int N, int K, int drop, int64_t* idx64, int32_t* idx32,
-                       void* workspace, cudaStream_t st);
+bool knn_feat_tc_supported(int N, int D, int K);
+int knn_feat_tc_launch(const float* feat, int B, int N, int D, int K, int drop, int64_t* idx64,
+                       int32_t* idx32, void* workspace, cudaStream_t st);
 }  // namespace hsp
 
 extern "C" size_t hsp_knn_feat_workspace_bytes(int B, int N) {
@@ -288,11 +289,11 @@ extern "C" int hsp_knn_feat(const float* feat, int B, int N, int D, int k, int d
   if (B == 0) return HSP_OK;
   if (!workspace || workspace_bytes < hsp_knn_feat_workspace_bytes(B, N)) return HSP_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  // D = 128: tensor-core filter (tcgen05 + TMEM) + exact FP32 refine, bit-identical results
+  // D = 128 (any N) and D = 256 (N <= 512): tensor-core filter (tcgen05 + TMEM) + exact FP32 refine, bit-identical results
   // (knn_feat_tc.cu).  HSP_KNN_FEAT_EXACT=1 forces the all-FP32 kernel below (A/B testing).
   static const bool force_exact = getenv("HSP_KNN_FEAT_EXACT") != nullptr;
-  if (D == 128 && K <= 64 && N <= 65535 && !force_exact && (((uintptr_t)feat) & 15) == 0)
-    return knn_feat_tc_launch(feat, B, N, K, drop_first, idx64, idx32, workspace, st);
+  if (knn_feat_tc_supported(N, D, K) && !force_exact && (((uintptr_t)feat) & 15) == 0)
+    return knn_feat_tc_launch(feat, B, N, D, K, drop_first, idx64, idx32, workspace, st);
   float* qn = (float*)workspace;
   sqnorm_rows_kernel<<<(B * N + 127) / 128, 128, 0, st>>>(feat, B * N, D, qn);
   HSP_LAUNCH_CHECK();

@@ -1,4 +1,4 @@
-// K2-TC — feature-space KNN (D = 128) as "tensor-core filter + exact refine".
+// K2-TC — feature-space KNN (D = 128; D = 256 for N <= 512) as "tensor-core filter + exact refine".
 //
 // Replaces get_neighbor_index(feature_map, k) (reference gcn3d.py:15-24, RF-F mode of
 // get_receptive_fields gcn3d.py:189-209) for D = 128 with results BIT-IDENTICAL to the exact
@@ -28,7 +28,7 @@ namespace hsp {
 namespace tc {
 
 constexpr int TR = 64;                      // rows per global tile
-constexpr int DK = 128;                     // feature dimension of this path
+constexpr int DK = 128;                     // features per MMA pass (a "d-half"); D = 128 or 256 (two passes)
 constexpr int KC = DK / 8;                  // 16-byte k-chunks per row
 constexpr int TILE_BYTES = KC * TR * 16;    // one (tile, hi|lo) block: 16 KB
 constexpr int QROWS = 128;                  // query rows per CTA = UMMA M
@@ -147,17 +147,19 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
 // ---------------------------------------------------------------- pre-pass
 // hi/lo split into the tiled UMMA layout.  One thread = one 16-byte k-chunk of one row.
 __global__ void __launch_bounds__(256)
-kf_split_kernel(const float* __restrict__ feat, int N, int T64, __nv_bfloat16* __restrict__ hi,
+kf_split_kernel(const float* __restrict__ feat, int N, int D, int T64, __nv_bfloat16* __restrict__ hi,
                 __nv_bfloat16* __restrict__ lo) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T64 * TR * KC) return;
-  const int row = t / KC, kc = t % KC;
+  const int kcs = D / 8, nd = D / DK;
+  if (t >= T64 * TR * kcs) return;
+  const int row = t / kcs, kcg = t % kcs;
+  const int h = kcg / KC, kc = kcg % KC;
   float v[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = 0.0f;
   if (row < N) {
-    const float4* p = reinterpret_cast<const float4*>(feat + ((size_t)b * N + row) * DK + kc * 8);
+    const float4* p = reinterpret_cast<const float4*>(feat + ((size_t)b * N + row) * D + kcg * 8);
     const float4 a = __ldg(p), c = __ldg(p + 1);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
   }
@@ -166,29 +168,30 @@ kf_split_kernel(const float* __restrict__ feat, int N, int T64, __nv_bfloat16* _
   __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&ul);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    const float2 hf = __bfloat1622float2(h);
-    h2[i] = h;
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(hh);
+    h2[i] = hh;
     l2[i] = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
   }
-  const size_t off = ((((size_t)b * T64 + row / TR) * KC + kc) * TR + (row % TR)) * 8;
+  // [object][64-row tile][d-half][k-chunk][row][8]
+  const size_t off = ((((((size_t)b * T64 + row / TR) * nd + h) * KC + kc) * TR) + (row % TR)) * 8;
   *reinterpret_cast<uint4*>(hi + off) = uh;
   *reinterpret_cast<uint4*>(lo + off) = ul;
 }
 
 // Exact |f|^2 (rounded squares added left to right, as knn_feat.cu) padded with +inf; per-object max.
 __global__ void __launch_bounds__(128)
-kf_norm_kernel(const float* __restrict__ feat, int N, int rows_pad, float* __restrict__ qn,
+kf_norm_kernel(const float* __restrict__ feat, int N, int D, int rows_pad, float* __restrict__ qn,
                float* __restrict__ qmax) {
   const int b = blockIdx.y;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows_pad) return;
   float s = INFINITY;
   if (r < N) {
-    const float4* p = reinterpret_cast<const float4*>(feat + ((size_t)b * N + r) * DK);
+    const float4* p = reinterpret_cast<const float4*>(feat + ((size_t)b * N + r) * D);
     s = 0.0f;
 #pragma unroll 4
-    for (int d4 = 0; d4 < DK / 4; ++d4) {
+    for (int d4 = 0; d4 < D / 4; ++d4) {
       const float4 v = __ldg(p + d4);
       if (d4 == 0) s = __fmul_rn(v.x, v.x); else s = __fadd_rn(s, __fmul_rn(v.x, v.x));
       s = __fadd_rn(s, __fmul_rn(v.y, v.y));
@@ -221,27 +224,10 @@ __device__ __forceinline__ void sort_regs(float (&m)[NS]) {
   }
 }
 
-// exact FP32 distance of the reference formula, one sequential FMA chain over d (knn_feat.cu order);
-// fi: query row (global, warp-uniform -> broadcast), sj: candidate row staged in shared memory
-__device__ __forceinline__ float exact_dist(const float* __restrict__ fi, const float* sj, float qi, float qj) {
-  const float4* a4 = reinterpret_cast<const float4*>(fi);
-  const float4* b4 = reinterpret_cast<const float4*>(sj);
-  float acc = 0.0f;
-#pragma unroll 8
-  for (int d4 = 0; d4 < DK / 4; ++d4) {
-    const float4 a = __ldg(a4 + d4), c = b4[d4];
-    acc = __fmaf_rn(a.x, c.x, acc);
-    acc = __fmaf_rn(a.y, c.y, acc);
-    acc = __fmaf_rn(a.z, c.z, acc);
-    acc = __fmaf_rn(a.w, c.w, acc);
-  }
-  return __fadd_rn(__fadd_rn(__fmul_rn(acc, -2.0f), qj), qi);
-}
-
 __global__ void __launch_bounds__(THREADS, 1)
 knn_feat_tc_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* __restrict__ glo,
-                   const float* __restrict__ qn, const float* __restrict__ qmax, int N, int T64, int K,
-                   uint2* __restrict__ surv, int* __restrict__ surv_cnt) {
+                   const float* __restrict__ qn, const float* __restrict__ qmax, int N, int T64, int K, int nd,
+                   float eps_rel, uint2* __restrict__ surv, int* __restrict__ surv_cnt) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sA_hi = smem;                                   // [KC][128][8] bf16   32 KB
   unsigned char* sA_lo = sA_hi + 2 * TILE_BYTES;                 //                      32 KB
@@ -249,14 +235,14 @@ knn_feat_tc_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* _
   float* s_qn = reinterpret_cast<float*>(sB + 4 * TILE_BYTES);   // [ROUND_COLS]
   uint2* s_list = reinterpret_cast<uint2*>(s_qn + ROUND_COLS);   // [128][LCAP] (approximate distance bits, index)
   int* s_cnt = reinterpret_cast<int*>(s_list + QROWS * LCAP);    // [128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_cnt + QROWS);   // [0..1] full, [2..3] empty, [4] A, [5] round done
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_cnt + QROWS);   // [0..1] full, [2..3] empty, [4] A full, [5] round done, [6] A free
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int b = blockIdx.y, qt = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rows_pad = T64 * TR;
-  const unsigned char* obj_hi = reinterpret_cast<const unsigned char*>(ghi) + (size_t)b * T64 * TILE_BYTES;
-  const unsigned char* obj_lo = reinterpret_cast<const unsigned char*>(glo) + (size_t)b * T64 * TILE_BYTES;
+  const unsigned char* obj_hi = reinterpret_cast<const unsigned char*>(ghi) + (size_t)b * T64 * nd * TILE_BYTES;
+  const unsigned char* obj_lo = reinterpret_cast<const unsigned char*>(glo) + (size_t)b * T64 * nd * TILE_BYTES;
   const float* qb = qn + (size_t)b * rows_pad;
 
   if (warp == 0) {   // TMEM: all 512 columns (one CTA per SM)
@@ -267,7 +253,7 @@ knn_feat_tc_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* _
   }
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) mbar_init(bars + i, 1);
+    for (int i = 0; i < 7; ++i) mbar_init(bars + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   s_cnt[tid] = 0;
@@ -276,22 +262,10 @@ knn_feat_tc_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* _
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *s_tmem;
 
-  // query block: two 64-row tiles -> [KC][128][8]   (64 bulk copies of 1 KB)
-  if (tid == 0) {
-    mbar_expect_tx(bars + 4, 4 * TILE_BYTES);
-    for (int h = 0; h < 2; ++h) {
-      const size_t src = (size_t)(2 * qt + h) * TILE_BYTES;
-      for (int kc = 0; kc < KC; ++kc) {
-        bulk_g2s(sA_hi + kc * 2048 + h * 1024, obj_hi + src + kc * 1024, 1024, bars + 4);
-        bulk_g2s(sA_lo + kc * 2048 + h * 1024, obj_lo + src + kc * 1024, 1024, bars + 4);
-      }
-    }
-  }
-
   const int i_row = qt * QROWS + tid;                 // this thread's query row (TMEM lane tid)
   const bool row_ok = i_row < N;
   const float qi = qb[min(i_row, rows_pad - 1)];
-  const float eps2 = 2.0f * EPS_REL * sqrtf(fmaxf(qi, 0.0f) * __ldg(qmax + b)) + 1e-30f;
+  const float eps2 = 2.0f * eps_rel * sqrtf(fmaxf(qi, 0.0f) * __ldg(qmax + b)) + 1e-30f;
   float thr = INFINITY;                               // running upper bound on the K-th smallest (d~ - qi)
   int cnt = 0;
   bool overflow = false;
@@ -302,6 +276,7 @@ knn_feat_tc_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* _
   const uint32_t idesc = umma_idesc(QROWS, TR);
   const int nsub_total = T64;                         // 64-candidate sub-tiles
   int it = 0;                                         // global sub-tile counter (pipeline phase tracking)
+  int a_loads = 0;                                    // query-block loads so far (thread 0 only)
   for (int sub0 = 0, round = 0; sub0 < nsub_total; sub0 += ROUND_COLS / TR, ++round) {
     const int nsub = min(ROUND_COLS / TR, nsub_total - sub0);
     const int col0 = sub0 * TR;
@@ -309,37 +284,55 @@ knn_feat_tc_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* _
     for (int c = tid; c < nsub * TR; c += THREADS) s_qn[c] = qb[col0 + c];
 
     if (tid == 0) {
-      if (round == 0) mbar_wait(bars + 4, 0);
-      auto load = [&](int s, int iter) {
-        const int st = iter & 1;
-        if (iter >= 2) mbar_wait(bars + 2 + st, ((iter >> 1) - 1) & 1);   // MMAs that read this stage are done
-        mbar_expect_tx(bars + st, 2 * TILE_BYTES);
-        bulk_g2s(sB + st * 2 * TILE_BYTES, obj_hi + (size_t)(sub0 + s) * TILE_BYTES, TILE_BYTES, bars + st);
-        bulk_g2s(sB + st * 2 * TILE_BYTES + TILE_BYTES, obj_lo + (size_t)(sub0 + s) * TILE_BYTES, TILE_BYTES,
-                 bars + st);
-      };
-      load(0, it);
-      for (int s = 0; s < nsub; ++s) {
-        const int iter = it + s, st = iter & 1;
-        if (s + 1 < nsub) load(s + 1, iter + 1);
-        mbar_wait(bars + st, (iter >> 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)(s * TR);
-        const uint32_t bh = smem_u32(sB + st * 2 * TILE_BYTES), bl = bh + TILE_BYTES;
-        const uint32_t ah = smem_u32(sA_hi), al = smem_u32(sA_lo);
-#pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          const uint32_t a0 = term == 2 ? al : ah, b0 = term == 1 ? bl : bh;
-#pragma unroll
-          for (int k = 0; k < DK / 16; ++k)
-            umma_bf16(d_tmem, umma_desc(a0 + k * 2 * 2048, 2048, 128), umma_desc(b0 + k * 2 * 1024, 1024, 128),
-                      idesc, (term | k) != 0);
+      for (int h = 0; h < nd; ++h) {
+        if (round == 0 || nd > 1) {
+          // query block of this d-half: two 64-row tiles -> [KC][128][8]   (64 bulk copies of 1 KB)
+          if (a_loads > 0) {                          // every MMA that reads the old block has retired
+            umma_commit(bars + 6);
+            mbar_wait(bars + 6, (a_loads - 1) & 1);
+          }
+          mbar_expect_tx(bars + 4, 4 * TILE_BYTES);
+          for (int hh = 0; hh < 2; ++hh) {
+            const size_t src = ((size_t)(2 * qt + hh) * nd + h) * TILE_BYTES;
+            for (int kc = 0; kc < KC; ++kc) {
+              bulk_g2s(sA_hi + kc * 2048 + hh * 1024, obj_hi + src + kc * 1024, 1024, bars + 4);
+              bulk_g2s(sA_lo + kc * 2048 + hh * 1024, obj_lo + src + kc * 1024, 1024, bars + 4);
+            }
+          }
+          mbar_wait(bars + 4, a_loads & 1);
+          ++a_loads;
         }
-        umma_commit(bars + 2 + st);                 // stage free when these MMAs retire
-        if (s == nsub - 1) umma_commit(bars + 5);   // round complete
+        auto load = [&](int s, int iter) {
+          const int st = iter & 1;
+          if (iter >= 2) mbar_wait(bars + 2 + st, ((iter >> 1) - 1) & 1);   // MMAs that read this stage are done
+          mbar_expect_tx(bars + st, 2 * TILE_BYTES);
+          const size_t src = ((size_t)(sub0 + s) * nd + h) * TILE_BYTES;
+          bulk_g2s(sB + st * 2 * TILE_BYTES, obj_hi + src, TILE_BYTES, bars + st);
+          bulk_g2s(sB + st * 2 * TILE_BYTES + TILE_BYTES, obj_lo + src, TILE_BYTES, bars + st);
+        };
+        load(0, it);
+        for (int s = 0; s < nsub; ++s) {
+          const int iter = it + s, st = iter & 1;
+          if (s + 1 < nsub) load(s + 1, iter + 1);
+          mbar_wait(bars + st, (iter >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d_tmem = tmem_base + (uint32_t)(s * TR);
+          const uint32_t bh = smem_u32(sB + st * 2 * TILE_BYTES), bl = bh + TILE_BYTES;
+          const uint32_t ah = smem_u32(sA_hi), al = smem_u32(sA_lo);
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t a0 = term == 2 ? al : ah, b0 = term == 1 ? bl : bh;
+#pragma unroll
+            for (int k = 0; k < DK / 16; ++k)
+              umma_bf16(d_tmem, umma_desc(a0 + k * 2 * 2048, 2048, 128), umma_desc(b0 + k * 2 * 1024, 1024, 128),
+                        idesc, (h | term | k) != 0);
+          }
+          umma_commit(bars + 2 + st);                 // stage free when these MMAs retire
+          if (s == nsub - 1 && h == nd - 1) umma_commit(bars + 5);   // round complete
+        }
+        it += nsub;
       }
     }
-    it += nsub;
     __syncthreads();                                  // s_qn visible; (tid 0 has issued everything)
     mbar_wait(bars + 5, round & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -448,20 +441,20 @@ __device__ __forceinline__ float orderable_to_float(uint32_t o) {
   return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
 }
 
-template <int NL>
+template <int NL, int DIM>
 __global__ void __launch_bounds__(RF_WARPS * 32)
 kf_refine_kernel(const float* __restrict__ feat, const float* __restrict__ qn, const float* __restrict__ qmax,
                  const uint2* __restrict__ surv, const int* __restrict__ surv_cnt, int N, int rows_pad, int K,
-                 int drop, int64_t* __restrict__ idx64, int32_t* __restrict__ idx32) {
+                 int drop, float eps_rel, int64_t* __restrict__ idx64, int32_t* __restrict__ idx32) {
   __shared__ __align__(16) float s_stage[RF_WARPS][32 * RF_PITCH];
   __shared__ uint64_t s_queue[RF_WARPS * 64];
   __shared__ uint16_t s_sel[RF_WARPS][LCAP + 4];
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * RF_WARPS + warp;
   if (i >= N) return;
-  const float* fb = feat + (size_t)b * N * DK;
+  const float* fb = feat + (size_t)b * N * DIM;
   const float* qb = qn + (size_t)b * rows_pad;
-  const float4* a4 = reinterpret_cast<const float4*>(fb + (size_t)i * DK);
+  const float4* a4 = reinterpret_cast<const float4*>(fb + (size_t)i * DIM);
   const float q_i = qb[i];
   float* stage = s_stage[warp];
   uint16_t* sel = s_sel[warp];
@@ -481,7 +474,7 @@ kf_refine_kernel(const float* __restrict__ feat, const float* __restrict__ qn, c
       o[u] = (lane + 32 * u < c_r) ? float_orderable(__uint_as_float(e[u].x)) : 0xffffffffu;
     }
     const uint32_t tau_o = warp_kth_smallest64(o[0], o[1], K, lane);
-    const float eps2 = 2.0f * EPS_REL * sqrtf(fmaxf(q_i, 0.0f) * __ldg(qmax + b)) + 1e-30f;
+    const float eps2 = 2.0f * eps_rel * sqrtf(fmaxf(q_i, 0.0f) * __ldg(qmax + b)) + 1e-30f;
     const float lim = orderable_to_float(tau_o) + eps2;
     int w = 0;
 #pragma unroll
@@ -502,13 +495,13 @@ kf_refine_kernel(const float* __restrict__ feat, const float* __restrict__ qn, c
     int jl = lane < nb ? (c_r >= 0 ? (int)sel[base + lane] : base + lane) : 0;
     jl = min(jl, N - 1);
     float acc = 0.0f;
-    for (int qd = 0; qd < DK; qd += RF_Q) {
+    for (int qd = 0; qd < DIM; qd += RF_Q) {
       __syncwarp();
       float4 t[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {      // rows 4u + sub: a warp request covers four 128-byte row pieces
         const int j = __shfl_sync(0xffffffffu, jl, 4 * u + sub);
-        t[u] = __ldg(reinterpret_cast<const float4*>(fb + (size_t)j * DK + qd) + l8);
+        t[u] = __ldg(reinterpret_cast<const float4*>(fb + (size_t)j * DIM + qd) + l8);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u)
@@ -544,7 +537,7 @@ kf_refine_kernel(const float* __restrict__ feat, const float* __restrict__ qn, c
 
 static size_t smem_bytes() {
   return (size_t)8 * TILE_BYTES + ROUND_COLS * sizeof(float) + (size_t)QROWS * LCAP * sizeof(uint2) +
-         QROWS * sizeof(int) + 6 * sizeof(uint64_t) + 16;
+         QROWS * sizeof(int) + 7 * sizeof(uint64_t) + 16;
 }
 
 }  // namespace tc
@@ -552,43 +545,55 @@ static size_t smem_bytes() {
 // T64: number of 64-row tiles, rounded up to an even count (a query block is two tiles).
 static int kf_tc_tiles(int N) { return 2 * ((N + 127) / 128); }
 
-size_t knn_feat_tc_workspace_bytes(int B, int N) {
-  const size_t T64 = kf_tc_tiles(N);
-  return (size_t)B * T64 * tc::TILE_BYTES * 2 + (size_t)B * T64 * tc::TR * sizeof(float) + (size_t)B * sizeof(float) +
-         (size_t)B * N * (tc::LCAP * sizeof(uint2) + sizeof(int)) + 1024;
+// D = 256 runs two d-halves that accumulate into the same TMEM columns, so every candidate of the
+// object must be resident at once: N <= 512.
+bool knn_feat_tc_supported(int N, int D, int K) {
+  // below ~128 points the all-FP32 kernel wins (measured: N = 64, D = 256: 0.05 vs 0.09 ms at B = 128)
+  return (D == 128 || (D == 256 && N <= tc::ROUND_COLS)) && K <= 64 && N >= 128 && N <= 65535;
 }
 
-// D = 128, K = k + drop <= 64, N <= 65535.
-int knn_feat_tc_launch(const float* feat, int B, int N, int K, int drop, int64_t* idx64, int32_t* idx32,
-                       void* workspace, cudaStream_t st) {
+size_t knn_feat_tc_workspace_bytes(int B, int N) {
+  const size_t T64 = kf_tc_tiles(N);
+  const size_t nd = N <= tc::ROUND_COLS ? 2 : 1;   // the query has no D: size for the widest supported case
+  return (size_t)B * T64 * nd * tc::TILE_BYTES * 2 + (size_t)B * T64 * tc::TR * sizeof(float) +
+         (size_t)B * sizeof(float) + (size_t)B * N * (tc::LCAP * sizeof(uint2) + sizeof(int)) + 1024;
+}
+
+int knn_feat_tc_launch(const float* feat, int B, int N, int D, int K, int drop, int64_t* idx64,
+                       int32_t* idx32, void* workspace, cudaStream_t st) {
   using namespace tc;
-  const int T64 = kf_tc_tiles(N);
+  const int T64 = kf_tc_tiles(N), nd = D / DK;
+  // error budget of the filter (file header): 2^-14 for D = 128; the accumulator and chain terms double
+  // with D, 2 * (1.1e-5 + 5.7e-6 + 1.5e-5) = 6.4e-5 -> 2^-13 for D = 256
+  const float eps_rel = D <= 128 ? EPS_REL : 2.0f * EPS_REL;
   unsigned char* ws = (unsigned char*)workspace;
   ws = (unsigned char*)(((uintptr_t)ws + 127) & ~(uintptr_t)127);
   __nv_bfloat16* hi = (__nv_bfloat16*)ws;
-  __nv_bfloat16* lo = (__nv_bfloat16*)(ws + (size_t)B * T64 * TILE_BYTES);
-  float* qn = (float*)(ws + (size_t)B * T64 * TILE_BYTES * 2);
+  __nv_bfloat16* lo = (__nv_bfloat16*)(ws + (size_t)B * T64 * nd * TILE_BYTES);
+  float* qn = (float*)(ws + (size_t)B * T64 * nd * TILE_BYTES * 2);
   float* qmax = qn + (size_t)B * T64 * TR;
   uintptr_t p = ((uintptr_t)(qmax + B) + 127) & ~(uintptr_t)127;
   uint2* surv = (uint2*)p;
   int* surv_cnt = (int*)(p + (size_t)B * N * LCAP * sizeof(uint2));
   if (cudaMemsetAsync(qmax, 0, sizeof(float) * B, st) != cudaSuccess) return HSP_ELAUNCH;
-  kf_norm_kernel<<<dim3((T64 * TR + 127) / 128, B), 128, 0, st>>>(feat, N, T64 * TR, qn, qmax);
+  kf_norm_kernel<<<dim3((T64 * TR + 127) / 128, B), 128, 0, st>>>(feat, N, D, T64 * TR, qn, qmax);
   HSP_LAUNCH_CHECK();
-  kf_split_kernel<<<dim3((T64 * TR * KC + 255) / 256, B), 256, 0, st>>>(feat, N, T64, hi, lo);
+  kf_split_kernel<<<dim3((T64 * TR * (D / 8) + 255) / 256, B), 256, 0, st>>>(feat, N, D, T64, hi, lo);
   HSP_LAUNCH_CHECK();
   const size_t smem = smem_bytes();
   if (cudaFuncSetAttribute(knn_feat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
       cudaSuccess)
     return HSP_ELAUNCH;
-  knn_feat_tc_kernel<<<dim3(T64 / 2, B), THREADS, smem, st>>>(hi, lo, qn, qmax, N, T64, K, surv, surv_cnt);
+  knn_feat_tc_kernel<<<dim3(T64 / 2, B), THREADS, smem, st>>>(hi, lo, qn, qmax, N, T64, K, nd, eps_rel, surv,
+                                                            surv_cnt);
   HSP_LAUNCH_CHECK();
-  if (K <= 32)
-    kf_refine_kernel<1><<<dim3((N + RF_WARPS - 1) / RF_WARPS, B), RF_WARPS * 32, 0, st>>>(
-        feat, qn, qmax, surv, surv_cnt, N, T64 * TR, K, drop, idx64, idx32);
-  else
-    kf_refine_kernel<2><<<dim3((N + RF_WARPS - 1) / RF_WARPS, B), RF_WARPS * 32, 0, st>>>(
-        feat, qn, qmax, surv, surv_cnt, N, T64 * TR, K, drop, idx64, idx32);
+  const dim3 rg((N + RF_WARPS - 1) / RF_WARPS, B);
+#define HSP_RF(NL_, D_)                                                                                   \
+  kf_refine_kernel<NL_, D_><<<rg, RF_WARPS * 32, 0, st>>>(feat, qn, qmax, surv, surv_cnt, N, T64 * TR, K, \
+                                                          drop, eps_rel, idx64, idx32)
+  if (D == 128) { if (K <= 32) HSP_RF(1, 128); else HSP_RF(2, 128); }
+  else          { if (K <= 32) HSP_RF(1, 256); else HSP_RF(2, 256); }
+#undef HSP_RF
   HSP_LAUNCH_CHECK();
   return HSP_OK;
 }
