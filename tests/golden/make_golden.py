@@ -161,7 +161,7 @@ def golden_e2e_eval(FLAGS, gcn3d):
     """PoseNet9D built and run as evaluation/evaluate.py does (FLAGS.train=0 before
     construction, .eval()), deterministic weights (oracle.synth.fill_params)."""
     sys.path.insert(0, ROOT)
-    from oracle.synth import fill_params, synth_batch
+    from hspose_b200.synth import fill_params, synth_batch
     from network.fs_net_repo.PoseNet9D import PoseNet9D
     FLAGS.train = 0
     arrays = {}
@@ -203,7 +203,7 @@ def golden_e2e_train(FLAGS, gcn3d):
     do_loss=True, sum of all loss terms, backward.  Dropout p=0 and augmentation
     probabilities 0 (device RNG streams differ between CPU and GPU)."""
     sys.path.insert(0, ROOT)
-    from oracle.synth import fill_params, synth_batch
+    from hspose_b200.synth import fill_params, synth_batch
     from network.HSPose import HSPose
     FLAGS.train = 1
     for n in ("aug_pc_pro", "aug_rt_pro", "aug_bb_pro", "aug_bc_pro"):
@@ -251,11 +251,39 @@ def golden_e2e_train(FLAGS, gcn3d):
     save("e2e_train", **arrays)
 
 
+def golden_augment(FLAGS):
+    """HSPose.data_augment of the reference (network/HSPose.py:185-256 over
+    datasets/data_augmentation.py:70-190) on CPU: once with every branch forced on (all
+    probabilities 1) and once with the shipped probabilities; RNG seeded before each call."""
+    sys.path.insert(0, ROOT)
+    from hspose_b200.synth import synth_batch
+    from network.HSPose import HSPose
+    FLAGS.train = 1
+    net = HSPose("PoseNet_only")
+    batch = synth_batch(8, 1028, seed=5, train=True)
+    arrays = {}
+    keep = {n: getattr(FLAGS, n) for n in ("aug_pc_pro", "aug_rt_pro", "aug_bb_pro", "aug_bc_pro")}
+    for tag, probs in (("all", dict(aug_pc_pro=1.0, aug_rt_pro=1.0, aug_bb_pro=1.0, aug_bc_pro=1.0)),
+                       ("default", dict(aug_pc_pro=0.2, aug_rt_pro=0.3, aug_bb_pro=0.3, aug_bc_pro=0.3))):
+        for n, v in probs.items():
+            setattr(FLAGS, n, v)
+        torch.manual_seed(777)
+        with torch.no_grad():
+            PC, R, t, s = net.data_augment(batch["PC"].clone(), batch["gt_R"].clone(), batch["gt_t"].clone(),
+                                           batch["gt_s"].clone(), batch["mean_shape"], batch["sym"],
+                                           batch["aug_bb"], batch["aug_rt_t"], batch["aug_rt_r"],
+                                           batch["model_point"].clone(), batch["nocs_scale"], batch["obj_id"])
+        arrays.update({f"{tag}_PC": PC, f"{tag}_R": R, f"{tag}_t": t, f"{tag}_s": s})
+    for n, v in keep.items():
+        setattr(FLAGS, n, v)
+    save("aug", **arrays)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     _args = sys.argv[1:]
     FLAGS, gcn3d = import_reference()
-    which = _args or ["knn", "ops", "e2e_eval", "e2e_train"]
+    which = _args or ["knn", "ops", "e2e_eval", "e2e_train", "aug"]
     if "knn" in which:
         golden_knn(gcn3d)
     if "ops" in which:
@@ -264,3 +292,5 @@ if __name__ == "__main__":
         golden_e2e_eval(FLAGS, gcn3d)
     if "e2e_train" in which:
         golden_e2e_train(FLAGS, gcn3d)
+    if "aug" in which:
+        golden_augment(FLAGS)

@@ -122,3 +122,38 @@ def test_oracle_train_forward_teacher_forced(golden):
     for n in ("recon", "face_dis", "face_f", "face_normal"):
         np.testing.assert_allclose(out[n][:, ::64].numpy(), g["out_" + n],
                                    atol=1e-3 if n == "face_normal" else 1e-4, err_msg=n)  # fn/|fn|, |fn| small
+
+
+@pytest.mark.parametrize("tag,probs", [("all", dict(aug_pc_pro=1.0, aug_rt_pro=1.0, aug_bb_pro=1.0, aug_bc_pro=1.0)),
+                                       ("default", dict(aug_pc_pro=0.2, aug_rt_pro=0.3, aug_bb_pro=0.3, aug_bc_pro=0.3))])
+def test_data_augment_matches_reference(golden, tag, probs):
+    """HSPose.data_augment (hs-pose_b200/augment.py, row-vector algebra) against the reference's
+    network/HSPose.py:185-256 run on CPU with the same seed: same RNG draws in the same order, same
+    Bernoulli gating, same deformations (bounding-box scaling, rotation/translation, the mug/bowl taper,
+    per-point noise) — with every branch forced on and with the shipped probabilities."""
+    import hspose_b200.flags as hf
+    from hspose_b200.HSPose import HSPose
+    from hspose_b200.synth import synth_batch
+    g = golden("aug")
+    F = hf.get_flags()
+    saved = {n: getattr(F, n) for n in probs}
+    saved_train = F.train
+    try:
+        F.train = 1
+        for n, v in probs.items():
+            setattr(F, n, v)
+        net = HSPose("PoseNet_only")
+        b = synth_batch(8, 1028, seed=5, train=True)
+        torch.manual_seed(777)
+        with torch.no_grad():
+            PC, R, t, s = net.data_augment(b["PC"].clone(), b["gt_R"].clone(), b["gt_t"].clone(), b["gt_s"].clone(),
+                                           b["mean_shape"], b["sym"], b["aug_bb"], b["aug_rt_t"], b["aug_rt_r"],
+                                           b["model_point"].clone(), b["nocs_scale"], b["obj_id"])
+        np.testing.assert_allclose(PC.numpy(), g[f"{tag}_PC"], atol=2e-6)
+        np.testing.assert_allclose(R.numpy(), g[f"{tag}_R"], atol=1e-6)
+        np.testing.assert_allclose(t.numpy(), g[f"{tag}_t"], atol=1e-6)
+        np.testing.assert_allclose(s.numpy(), g[f"{tag}_s"], atol=1e-6)
+    finally:
+        F.train = saved_train
+        for n, v in saved.items():
+            setattr(F, n, v)
