@@ -212,7 +212,7 @@ def dram_traffic(name, a):
 
 # what actually bounds each hand-written kernel (ncu evidence: profiles/*_ncu_full_summary.md)
 LIMITER = {
-    "hsp_graph_conv_bwd": "L2 atomic (RED.f32) throughput: N*S*C scattered adds per object; DRAM 19 %, issue 17 %",
+    "hsp_graph_conv_bwd": "L2 atomic (RED.f32) throughput: N*S*C scattered adds per object; DRAM 16-19 %, issue 16-18 %",
     "hsp_graph_conv_fwd": "instruction issue (N*k*S*C element ops from L2-resident rows); DRAM 7 %, issue 68 %",
     "hsp_knn_feat": "tcgen05 filter epilogue + exact-refine L2 gathers; DRAM 2 %, tensor pipe 14 %",
     "hsp_knn3": "ALU pipe (selection network); DRAM 0 %",
