@@ -438,17 +438,30 @@ surface_conv_bwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict
     stage_tile(xyz + (size_t)b * N * 3, idx + (size_t)b * N * k, i0, npts, k, s_idx, s_r);
     __syncthreads();
     if (c < C) {
-      for (int p = 0; p < npts; ++p) {
-        const size_t row = (size_t)b * N + i0 + p;
-        const float gs = __fdiv_rn(gout[row * C + c], (float)S);
+      // all winners and gradients of the tile are fetched first (8 x (S + 1) independent loads in
+      // flight per thread): the kernel is a latency-bound stream of 1-byte gathers otherwise
+      unsigned char am[GC_PT][S];
+      float gv[GC_PT];
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-          const int n = argmax[row * SC + s * C + c];   // 255: relu killed every neighbour
-          if (n < k) {
-            const float* r = s_r + 3 * (p * k + n);
-            gx[s] = fmaf(gs, r[0], gx[s]);
-            gy[s] = fmaf(gs, r[1], gy[s]);
-            gz[s] = fmaf(gs, r[2], gz[s]);
+      for (int p = 0; p < GC_PT; ++p) {
+        const size_t row = (size_t)b * N + i0 + (p < npts ? p : 0);
+        gv[p] = gout[row * C + c];
+#pragma unroll
+        for (int s = 0; s < S; ++s) am[p][s] = argmax[row * SC + s * C + c];
+      }
+#pragma unroll
+      for (int p = 0; p < GC_PT; ++p) {
+        if (p < npts) {
+          const float gs = __fdiv_rn(gv[p], (float)S);
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            const int n = am[p][s];                       // 255: relu killed every neighbour
+            if (n < k) {
+              const float* r = s_r + 3 * (p * k + n);
+              gx[s] = fmaf(gs, r[0], gx[s]);
+              gy[s] = fmaf(gs, r[1], gy[s]);
+              gz[s] = fmaf(gs, r[2], gz[s]);
+            }
           }
         }
       }
