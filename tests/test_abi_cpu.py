@@ -70,3 +70,38 @@ def test_product_path_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_hspose_boundary_error_behaviour_and_build_params():
+    """Reference conventions at the module boundary (network/HSPose.py:23-50,258-275,
+    engine/organize_loss.py:13): unknown stages raise NotImplementedError, a missing point cloud is
+    not silently sampled, build_params returns the single parameter group engine/train.py:47 expects."""
+    import hspose_b200.flags as hf
+    from hspose_b200.HSPose import HSPose, control_loss
+    with pytest.raises(NotImplementedError):
+        control_loss("no_such_stage")
+    with pytest.raises(NotImplementedError):
+        HSPose("no_such_stage")
+    net = HSPose("PoseNet_only")
+    with pytest.raises(NotImplementedError):
+        net(PC=None, obj_id=torch.zeros(1))
+    groups = net.build_params(training_stage_freeze=[])
+    assert len(groups) == 1 and groups[0]["lr"] == float(hf.get_flags().lr) * hf.get_flags().lr_pose
+    n = sum(p.numel() for p in groups[0]["params"])
+    assert n == 9709871            # SURVEY Appendix B: train build
+    frozen = HSPose("PoseNet_only").build_params(training_stage_freeze=["pose"])
+    assert sum(1 for _ in frozen[0]["params"]) == 0
+
+
+def test_flags_proxy_follows_the_reference_namespace_when_present():
+    """FLAGS reads resolve at access time (the reference mutates FLAGS.train between construction and
+    forward, evaluation/evaluate.py:39); stand-alone the reference defaults are used."""
+    import hspose_b200.flags as hf
+    F = hf.get_flags()
+    assert F.gcn_n_num == 20 and F.gcn_sup_num == 7 and F.random_points == 1028 and F.feat_c_R == 1286
+    old = F.train
+    try:
+        hf.FLAGS.train = 0
+        assert hf.get_flags().train == 0 and hf.FLAGS.train == 0
+    finally:
+        hf.FLAGS.train = old
