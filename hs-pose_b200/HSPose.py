@@ -7,11 +7,10 @@ evaluation/evaluate.py:58-104 run unchanged and published checkpoints load
 with strict=True.  The feature extractor underneath is the sm_100a kernel
 stack (gcn3d / FaceRecon / PoseNet9D of this package).
 
-Losses: `fs_net_loss` is native (losses.py).  recon_6face / geo / prop are
-out of the kernel scope: they are taken from the reference tree
-when it is importable (drop-in use) and otherwise omitted (empty dicts).  An
-optional Chamfer(recon, PC) term (BASELINE.json config 3) is added under
-fsnet_loss['Chamfer'] when `chamfer_w > 0`.
+Losses: all four groups (fs_net, recon_6face, geo, prop — the 19 scalar terms
+engine/train.py:96-97 sums) are native restatements in losses.py; nothing is
+imported from the reference tree.  An optional Chamfer(recon, PC) term
+(BASELINE.json config 3) is added under fsnet_loss['Chamfer'] when `chamfer_w > 0`.
 """
 import torch
 import torch.nn as nn
@@ -19,7 +18,8 @@ import torch.nn as nn
 from . import augment
 from .PoseNet9D import PoseNet9D
 from .flags import FLAGS
-from .losses import chamfer_recon_loss, fs_net_loss, get_gt_v
+from .losses import (chamfer_recon_loss, fs_net_loss, geo_transform_loss, get_gt_v, prop_rot_loss,
+                     recon_6face_loss)
 
 
 def control_loss(train_stage):
@@ -32,17 +32,6 @@ def control_loss(train_stage):
     raise NotImplementedError
 
 
-def _reference_losses():
-    """recon_6face_loss, geo_transform_loss, prop_rot_loss from the reference tree, if importable."""
-    try:
-        from losses.recon_loss import recon_6face_loss
-        from losses.geometry_loss import geo_transform_loss
-        from losses.prop_loss import prop_rot_loss
-        return recon_6face_loss(), geo_transform_loss(), prop_rot_loss()
-    except Exception:
-        return None, None, None
-
-
 class HSPose(nn.Module):
     def __init__(self, train_stage, chamfer_w=0.0):
         super(HSPose, self).__init__()
@@ -50,7 +39,9 @@ class HSPose(nn.Module):
         self.train_stage = train_stage
         self.chamfer_w = chamfer_w
         self.loss_fs_net = fs_net_loss()
-        self.loss_recon, self.loss_geo, self.loss_prop = _reference_losses()
+        self.loss_recon = recon_6face_loss()
+        self.loss_geo = geo_transform_loss()
+        self.loss_prop = prop_rot_loss()
         self.name_fs_list, self.name_recon_list, \
             self.name_geo_list, self.name_prop_list = control_loss(self.train_stage)
 
@@ -90,19 +81,18 @@ class HSPose(nn.Module):
         if self.chamfer_w > 0 and recon is not None:
             fsnet_loss['Chamfer'] = chamfer_recon_loss(recon, PC, self.chamfer_w)
 
-        prop_loss, recon_loss, geo_loss = {}, {}, {}
-        if self.loss_prop is not None:
+        if True:
             pred_prop_list = {'Recon': recon, 'Rot1': p_green_R, 'Rot2': p_red_R, 'Tran': Pred_T,
                               'Scale': Pred_s, 'Rot1_f': f_green_R.detach(), 'Rot2_f': f_red_R.detach()}
             gt_prop_list = {'Points': PC, 'R': gt_R, 'T': gt_t, 'Mean_shape': mean_shape}
             prop_loss = self.loss_prop(self.name_prop_list, pred_prop_list, gt_prop_list, sym)
-        if self.loss_recon is not None:
+        if True:
             pred_recon_list = {'F_n': face_normal, 'F_d': face_dis, 'F_c': face_f, 'Rot1': p_green_R,
                                'Rot1_f': f_green_R.detach(), 'Rot2': p_red_R, 'Rot2_f': f_red_R.detach(),
                                'Tran': Pred_T, 'Size': Pred_s}
             gt_recon_list = {'R': gt_R, 'T': gt_t, 'Size': gt_s, 'Mean_shape': mean_shape, 'Points': PC}
             recon_loss = self.loss_recon(self.name_recon_list, pred_recon_list, gt_recon_list, sym, obj_id)
-        if self.loss_geo is not None:
+        if True:
             pred_geo_list = {'Rot1': p_green_R, 'Rot2': p_red_R, 'Tran': Pred_T, 'Size': Pred_s,
                              'Rot1_f': f_green_R.detach(), 'Rot2_f': f_red_R.detach()}
             gt_geo_list = {'Points': PC, 'R': gt_R, 'T': gt_t, 'Mean_shape': mean_shape}

@@ -438,3 +438,32 @@ extern "C" int hsp_bn_relu_bwd(const void* x, int ldx, const void* dy, int lddy,
   }
   return HSP_OK;
 }
+
+// Forward with the statistics partials already produced by the GEMM epilogue (gemm_tc.cu): finalize
+// (fixed-order sums) + normalise/ReLU.  `partials` is (nblocks, 2, C): column sums and sums of squares.
+extern "C" int hsp_bn_apply_fwd(const void* x, int ldx, int M, int C, int dtype, const float* partials,
+                                int nblocks, const float* gamma, const float* beta, float eps,
+                                float momentum, int relu, float* running_mean, float* running_var,
+                                float* mean, float* invstd, float* scale_shift, void* y, int ldy,
+                                void* stream) {
+  using namespace hsp;
+  if (bn_bad(x, M, C, ldx, dtype) || bn_bad(y, M, C, ldy, dtype) || !mean || !invstd || !scale_shift ||
+      !partials || nblocks <= 0)
+    return HSP_EINVAL;
+  const BnGeom g = bn_geom(M, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(g.ctiles, g.rchunks);
+  float* scale = scale_shift;
+  float* shift = scale_shift + C;
+  bn_finalize_fwd_kernel<<<(C + BN_FC - 1) / BN_FC, BN_FC * BN_FG, 0, st>>>(
+      partials, nblocks, M, C, eps, momentum, gamma, beta, mean, invstd, scale, shift, running_mean, running_var);
+  HSP_LAUNCH_CHECK();
+  if (dtype == HSP_DTYPE_BF16)
+    bn_apply_kernel<__nv_bfloat16><<<grid, BN_THREADS, 0, st>>>(
+        (const __nv_bfloat16*)x, ldx, scale, shift, relu, M, C, g.ct, (__nv_bfloat16*)y, ldy);
+  else
+    bn_apply_kernel<float><<<grid, BN_THREADS, 0, st>>>((const float*)x, ldx, scale, shift, relu, M, C,
+                                                        g.ct, (float*)y, ldy);
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}

@@ -17,6 +17,9 @@ _DEFAULTS = dict(
     aug_pc_pro=0.2, aug_pc_r=0.2, aug_rt_pro=0.3, aug_bb_pro=0.3, aug_bc_pro=0.3,
     fsnet_loss_type="l1", rot_1_w=8.0, rot_2_w=8.0, rot_regular=4.0, tran_w=8.0, size_w=8.0,
     recon_w=8.0, r_con_w=1.0, lr=1e-4, lr_pose=1.0, sample_method="basic",
+    recon_n_w=3.0, recon_d_w=3.0, recon_v_w=1.0, recon_s_w=0.3, recon_f_w=1.0, recon_bb_r_w=1.0,
+    recon_bb_t_w=1.0, recon_bb_s_w=1.0, recon_bb_self_w=1.0, recon_c_w=0.0, geo_p_w=1.0, geo_f_w=0.1,
+    prop_pm_w=2.0, prop_sym_w=1.0, prop_r_reg_w=1.0,
 )
 
 _standalone = types.SimpleNamespace(**_DEFAULTS)

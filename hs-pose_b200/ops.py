@@ -706,6 +706,48 @@ def multi_linear_bn_relu(x, blocks):
     return list(_MultiLinearBnRelu.apply(x, buffers, *params))
 
 
+# ------------------------------------------------------------ K6: tensor-core GEMM
+def gemm_splits(M, N, K):
+    return int(_lib.load().hsp_gemm_bf16_splits(M, N, K, 1))
+
+
+def gemm_bf16(a, b, a_mn=False, b_mn=False, bias=None, out=None, out_dtype=torch.bfloat16, splits=1,
+              stats=False, tile_n=0, ctas=0):
+    """K6: out[M,N] (+bias) = A . B^T on tcgen05 tensor cores (bf16 operands, fp32 accumulate).
+
+    a: (M,K) [a_mn=False] or (K,M) [a_mn=True];  b: (N,K) [b_mn=False] or (K,N) [b_mn=True]; both bf16
+    2-D with unit inner stride (row pitch may exceed the width: column slices are fine).
+    out_dtype bf16 | fp32; splits > 1 (fp32 only) returns the sum of the split-K planes.
+    stats=True also returns the (ceil(M/128), 2, N) BatchNorm partials of the stored values."""
+    for t, name in ((a, "a"), (b, "b")):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise _lib.HSPoseLibraryError(f"gemm_bf16: {name} must be a CUDA tensor (no CPU path)")
+        if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
+            raise TypeError(f"gemm_bf16: {name} must be a 2-D bf16 matrix with unit inner stride")
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    if K != Kb:
+        raise ValueError(f"gemm_bf16: reduction mismatch {K} vs {Kb}")
+    f32 = out_dtype == torch.float32
+    with torch.cuda.device(a.device):
+        if out is None:
+            ldo = N + ((-N) % (4 if f32 else 8))
+            buf = torch.empty((splits, M, ldo) if splits > 1 else (M, ldo), dtype=out_dtype, device=a.device)
+        else:
+            buf, ldo = out, out.stride(-2)
+        st = torch.empty((M + 127) // 128, 2, N, dtype=torch.float32, device=a.device) if stats else None
+        if bias is not None:
+            bias = _need(bias, torch.float32, "bias")
+        _call("hsp_gemm_bf16", _p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), M, N, K,
+              _p(bias), _p(buf), ldo, int(f32), splits, _p(st), tile_n, ctas, _stream())
+    res = buf
+    if splits > 1:
+        res = buf[0] if splits == 1 else buf.sum(dim=0)
+    if out is None and res.shape[-1] != N:
+        res = res[..., :N]
+    return (res, st) if stats else res
+
+
 # ---------------------------------------------------------------- chamfer
 class _Chamfer(torch.autograd.Function):
     @staticmethod

@@ -233,6 +233,42 @@ int hsp_bn_relu_bwd(const void* x, int ldx, const void* dy, int lddy, int M, int
                     int lddx, float* dx_colsum, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* Forward with the statistics partials already produced by hsp_gemm_bf16's epilogue: `partials`
+ * is (nblocks, 2, C) column sums / sums of squares over disjoint row blocks covering the M rows. */
+int hsp_bn_apply_fwd(const void* x, int ldx, int M, int C, int dtype, const float* partials,
+                     int nblocks, const float* gamma, const float* beta, float eps, float momentum,
+                     int relu, float* running_mean, float* running_var, float* mean, float* invstd,
+                     float* scale_shift, void* y, int ldy, void* stream);
+
+/* ------------------------------------------------------------------ K6 ---
+ * Dense per-point MLP contraction on the tensor cores (tcgen05.mma, TMA tensor loads,
+ * TMEM accumulators):   out[M,N] (+ bias[N]) = A[M,K] . B[N,K]^T,  bf16 operands, fp32
+ * accumulation, bf16 or fp32 output.  Replaces the library GEMM behind every
+ * Conv1d(kernel_size=1) / `@` of the reference's dense stages, forward and backward:
+ *   heads conv1..2           PoseR.py:27-34, PoseTs.py:32-39
+ *   conv1d_block / recon / face stacks   FaceRecon.py:38-68,114-124
+ *   feature_map @ weights + bias         gcn3d.py:171
+ *   STE_layer / conv2 (1x1)              gcn3d.py:85,112,149,186
+ * Operand majors: *_mn_major = 0 -> the matrix is stored (rows = M|N, cols = K) with leading
+ * dimension ld (K contiguous: activations as A, nn.Linear weights (out,in) as B);
+ * = 1 -> stored (rows = K, cols = M|N) (the M|N index contiguous: the transposed operands of
+ * dgrad / wgrad, and gcn3d's (in,out) `weights`), so nothing is transposed in memory.
+ * ld* in elements; pointers and row pitches 16-byte aligned.
+ *   splits > 1 (fp32 output only): split-K; plane s of `out` (M*ldo elements each) receives the
+ *     partial product of k-slice s — the caller adds the planes in order (deterministic).
+ *     hsp_gemm_bf16_splits() returns the factor the library would choose.
+ *   stats (optional, bf16 output): (ceil(M/128), 2, N) floats — per 128-row block the column
+ *     sums and sums of squares of the values AS STORED; this is the partial layout
+ *     hsp_bn_apply_fwd() consumes, so BatchNorm needs no statistics pass of its own.
+ *   tile_n in {64,128,256} and ctas in {1,2} pick the tile (0 = library default).            */
+int hsp_gemm_bf16_splits(int M, int N, int K, int out_f32);
+/* Diagnostics for profiling (results are WRONG while non-zero): bit 0 skips the epilogue's staging
+ * writes and stores, bit 1 the MMAs, bit 2 the TMA loads.  Returns the previous value.          */
+int hsp_gemm_debug(int flags);
+int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major,
+                  int M, int N, int K, const float* bias, void* out, int ldo, int out_f32,
+                  int splits, float* stats, int tile_n, int ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
