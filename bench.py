@@ -46,11 +46,15 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=4, help="objects per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of one CUDA graph")
+    ap.add_argument("--losses", default="all", choices=["all", "fsnet"],
+                    help="all = the 19 terms engine/train.py sums (fs_net + recon_6face + geo + prop) + Chamfer; "
+                         "fsnet = fs_net + Chamfer only (the round-1 workload)")
     return ap.parse_args()
 
 
 def workload_config(args, world):
-    return {"workload": f"train step (fwd+bwd+Adam, fs_net+Chamfer losses) batch={args.batch}/GPU "
+    losses = "fs_net + recon_6face + geo + prop (19 terms) + Chamfer" if args.losses == "all" else "fs_net + Chamfer"
+    return {"workload": f"train step (fwd+bwd+Adam, {losses} losses) batch={args.batch}/GPU "
                         f"N={N_PTS} k={K_NBR} S={S_SUP}",
             "global_batch": args.batch * world, "n_points": N_PTS, "k": K_NBR,
             "precision": "bf16 autocast dense GEMMs; fp32 KNN/graph-conv kernels"
@@ -294,7 +298,8 @@ def run_b200(args):
     torch.backends.cudnn.allow_tf32 = False
 
     torch.manual_seed(0)                       # identical weights on every rank
-    model = HSPose("PoseNet_only", chamfer_w=1.0).to(dev).train()
+    groups = ("fsnet", "recon", "geo", "prop") if args.losses == "all" else ("fsnet",)
+    model = HSPose("PoseNet_only", chamfer_w=1.0, loss_groups=groups).to(dev).train()
     parallel.seed_all(1234)                    # same Pool_layer permutations on every rank
     amp = args.precision == "bf16"
     trainer = TrainStep(model, lr=1e-4, clip=5.0, amp=amp, graph=not args.no_graph)

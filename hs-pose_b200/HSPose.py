@@ -15,7 +15,7 @@ imported from the reference tree.  An optional Chamfer(recon, PC) term
 import torch
 import torch.nn as nn
 
-from . import augment
+from . import augment, ops
 from .PoseNet9D import PoseNet9D
 from .flags import FLAGS
 from .losses import (chamfer_recon_loss, fs_net_loss, geo_transform_loss, get_gt_v, prop_rot_loss,
@@ -33,7 +33,9 @@ def control_loss(train_stage):
 
 
 class HSPose(nn.Module):
-    def __init__(self, train_stage, chamfer_w=0.0):
+    def __init__(self, train_stage, chamfer_w=0.0, loss_groups=("fsnet", "recon", "geo", "prop")):
+        """`loss_groups` (extension, default = the reference's behaviour): which of the four loss groups
+        are evaluated; a group left out comes back as an empty dict."""
         super(HSPose, self).__init__()
         self.posenet = PoseNet9D()
         self.train_stage = train_stage
@@ -44,6 +46,7 @@ class HSPose(nn.Module):
         self.loss_prop = prop_rot_loss()
         self.name_fs_list, self.name_recon_list, \
             self.name_geo_list, self.name_prop_list = control_loss(self.train_stage)
+        self.loss_groups = tuple(loss_groups)
 
     def forward(self, PC=None, depth=None, obj_id=None, camK=None,
                 gt_R=None, gt_t=None, gt_s=None, mean_shape=None, gt_2D=None, sym=None, aug_bb=None,
@@ -77,22 +80,29 @@ class HSPose(nn.Module):
         pred_fsnet_list = {'Rot1': p_green_R, 'Rot1_f': f_green_R, 'Rot2': p_red_R, 'Rot2_f': f_red_R,
                            'Recon': recon, 'Tran': Pred_T, 'Size': Pred_s}
         gt_fsnet_list = {'Rot1': gt_green_v, 'Rot2': gt_red_v, 'Recon': PC, 'Tran': gt_t, 'Size': gt_s}
-        fsnet_loss = self.loss_fs_net(self.name_fs_list, pred_fsnet_list, gt_fsnet_list, sym)
+        if self._fused_losses_ok(PC, recon):
+            return output_dict, self._fused_losses(PC, recon, p_green_R, p_red_R, f_green_R, f_red_R, Pred_T, Pred_s,
+                                                   gt_R, gt_t, gt_s, mean_shape, sym, obj_id)
+
+        fsnet_loss = {}
+        if "fsnet" in self.loss_groups:
+            fsnet_loss = self.loss_fs_net(self.name_fs_list, pred_fsnet_list, gt_fsnet_list, sym)
         if self.chamfer_w > 0 and recon is not None:
             fsnet_loss['Chamfer'] = chamfer_recon_loss(recon, PC, self.chamfer_w)
 
-        if True:
+        prop_loss, recon_loss, geo_loss = {}, {}, {}
+        if "prop" in self.loss_groups:
             pred_prop_list = {'Recon': recon, 'Rot1': p_green_R, 'Rot2': p_red_R, 'Tran': Pred_T,
                               'Scale': Pred_s, 'Rot1_f': f_green_R.detach(), 'Rot2_f': f_red_R.detach()}
             gt_prop_list = {'Points': PC, 'R': gt_R, 'T': gt_t, 'Mean_shape': mean_shape}
             prop_loss = self.loss_prop(self.name_prop_list, pred_prop_list, gt_prop_list, sym)
-        if True:
+        if "recon" in self.loss_groups:
             pred_recon_list = {'F_n': face_normal, 'F_d': face_dis, 'F_c': face_f, 'Rot1': p_green_R,
                                'Rot1_f': f_green_R.detach(), 'Rot2': p_red_R, 'Rot2_f': f_red_R.detach(),
                                'Tran': Pred_T, 'Size': Pred_s}
             gt_recon_list = {'R': gt_R, 'T': gt_t, 'Size': gt_s, 'Mean_shape': mean_shape, 'Points': PC}
             recon_loss = self.loss_recon(self.name_recon_list, pred_recon_list, gt_recon_list, sym, obj_id)
-        if True:
+        if "geo" in self.loss_groups:
             pred_geo_list = {'Rot1': p_green_R, 'Rot2': p_red_R, 'Tran': Pred_T, 'Size': Pred_s,
                              'Rot1_f': f_green_R.detach(), 'Rot2_f': f_red_R.detach()}
             gt_geo_list = {'Points': PC, 'R': gt_R, 'T': gt_t, 'Mean_shape': mean_shape}
@@ -101,6 +111,30 @@ class HSPose(nn.Module):
         loss_dict = {'fsnet_loss': fsnet_loss, 'recon_loss': recon_loss, 'geo_loss': geo_loss,
                      'prop_loss': prop_loss}
         return output_dict, loss_dict
+
+    # ---- K8: the whole 19-term loss graph as two launches each way (ops.fused_losses)
+    fused_losses = True    # set False to evaluate the losses with the tensor-algebra modules of losses.py
+
+    def _fused_losses_ok(self, PC, recon):
+        return (self.fused_losses and PC.is_cuda and recon is not None and self.train_stage == 'PoseNet_only'
+                and FLAGS.fsnet_loss_type == 'l1' and FLAGS.prop_sym_w > 0
+                and getattr(self.posenet, "face_raw", None) is not None)
+
+    def _fused_losses(self, PC, recon, p_green_R, p_red_R, f_green_R, f_red_R, Pred_T, Pred_s, gt_R, gt_t, gt_s,
+                      mean_shape, sym, obj_id):
+        weights = [getattr(FLAGS, n) for n in ops.LOSS_WEIGHT_FLAGS]
+        t = ops.fused_losses(weights, self.posenet.face_raw, recon, p_green_R, p_red_R, f_green_R, f_red_R, Pred_T,
+                             Pred_s, PC, gt_R, gt_t, gt_s, mean_shape, sym, obj_id)
+        g = self.loss_groups
+        fs = {k: t[k] for k in ("Rot1", "Rot1_cos", "Rot2", "Rot2_cos", "Rot_r_a", "Tran", "Size", "R_con")} \
+            if "fsnet" in g else {}
+        if self.chamfer_w > 0:
+            fs['Chamfer'] = chamfer_recon_loss(recon, PC, self.chamfer_w)
+        rec = {k: t[k] for k in ("recon_per_p", "recon_p_f", "recon_point_vote", "recon_point_r", "recon_point_t",
+                                 "recon_point_s", "recon_point_self")} if "recon" in g else {}
+        geo = {"geo_point": t["geo_point"]} if "geo" in g else {}
+        prop = {k: t[k] for k in ("Prop_pm", "Prop_sym_recon", "Prop_sym_rt")} if "prop" in g else {}
+        return {'fsnet_loss': fs, 'recon_loss': rec, 'geo_loss': geo, 'prop_loss': prop}
 
     def data_augment(self, PC, gt_R, gt_t, gt_s, mean_shape, sym, aug_bb, aug_rt_t, aug_rt_r,
                      model_point, nocs_scale, obj_ids, check_points=False):

@@ -32,8 +32,10 @@ class PoseNet9D(nn.Module):
         recon, face, feat = self.face_recon(centred, obj_id)
         joint = self.face_recon.joint_out or [None, None, None]
 
+        self.face_raw = None
         if FLAGS.train:
             recon, face = recon.float() + mean, face.float()
+            self.face_raw = face      # (bs, N, 30) fp32: the fused loss kernel (K8) starts from the raw head output
             face_normal = face[:, :, :18].view(bs, p_num, 6, 3)
             face_normal = face_normal / torch.norm(face_normal, dim=-1, keepdim=True)
             face_dis = face[:, :, 18:24]

@@ -170,7 +170,8 @@ bn_reduce_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, int
 // (deterministic).  C/8 CTAs: wide enough that the finalize costs a few microseconds.
 constexpr int BN_FC = 8, BN_FG = 32;
 __device__ __forceinline__ bool bn_sum_partials(const float* __restrict__ partial, int rchunks,
-                                                int C, int& c, double& s, double& q) {
+                                                int C, int& c, double& s, double& q, int ldp = 0) {
+  if (ldp == 0) ldp = C;    // row pitch of a partial plane (>= C when the planes are column slices)
   __shared__ double sh[2][BN_FG][BN_FC];
   const int cx = threadIdx.x % BN_FC, ry = threadIdx.x / BN_FC;
   c = blockIdx.x * BN_FC + cx;
@@ -178,8 +179,8 @@ __device__ __forceinline__ bool bn_sum_partials(const float* __restrict__ partia
   if (c < C) {
 #pragma unroll 8
     for (int r = ry; r < rchunks; r += BN_FG) {
-      a += (double)__ldg(partial + ((size_t)r * 2) * C + c);
-      b += (double)__ldg(partial + ((size_t)r * 2 + 1) * C + c);
+      a += (double)__ldg(partial + ((size_t)r * 2) * ldp + c);
+      b += (double)__ldg(partial + ((size_t)r * 2 + 1) * ldp + c);
     }
   }
   sh[0][ry][cx] = a;
@@ -199,10 +200,10 @@ bn_finalize_fwd_kernel(const float* __restrict__ partial, int rchunks, int M, in
                        const float* __restrict__ beta, float* __restrict__ mean,
                        float* __restrict__ invstd, float* __restrict__ scale,
                        float* __restrict__ shift, float* __restrict__ running_mean,
-                       float* __restrict__ running_var) {
+                       float* __restrict__ running_var, int ldp = 0) {
   int c;
   double s, q;
-  if (!bn_sum_partials(partial, rchunks, C, c, s, q)) return;
+  if (!bn_sum_partials(partial, rchunks, C, c, s, q, ldp)) return;
   const double m = s / M;
   double var = q / M - m * m;
   if (var < 0.0) var = 0.0;
@@ -440,15 +441,15 @@ extern "C" int hsp_bn_relu_bwd(const void* x, int ldx, const void* dy, int lddy,
 }
 
 // Forward with the statistics partials already produced by the GEMM epilogue (gemm_tc.cu): finalize
-// (fixed-order sums) + normalise/ReLU.  `partials` is (nblocks, 2, C): column sums and sums of squares.
+// (fixed-order sums) + normalise/ReLU.  `partials` is (nblocks, 2, C) with row pitch ldp >= C: column sums and sums of squares.
 extern "C" int hsp_bn_apply_fwd(const void* x, int ldx, int M, int C, int dtype, const float* partials,
-                                int nblocks, const float* gamma, const float* beta, float eps,
+                                int nblocks, int ldp, const float* gamma, const float* beta, float eps,
                                 float momentum, int relu, float* running_mean, float* running_var,
                                 float* mean, float* invstd, float* scale_shift, void* y, int ldy,
                                 void* stream) {
   using namespace hsp;
   if (bn_bad(x, M, C, ldx, dtype) || bn_bad(y, M, C, ldy, dtype) || !mean || !invstd || !scale_shift ||
-      !partials || nblocks <= 0)
+      !partials || nblocks <= 0 || ldp < C)
     return HSP_EINVAL;
   const BnGeom g = bn_geom(M, C);
   cudaStream_t st = (cudaStream_t)stream;
@@ -456,7 +457,8 @@ extern "C" int hsp_bn_apply_fwd(const void* x, int ldx, int M, int C, int dtype,
   float* scale = scale_shift;
   float* shift = scale_shift + C;
   bn_finalize_fwd_kernel<<<(C + BN_FC - 1) / BN_FC, BN_FC * BN_FG, 0, st>>>(
-      partials, nblocks, M, C, eps, momentum, gamma, beta, mean, invstd, scale, shift, running_mean, running_var);
+      partials, nblocks, M, C, eps, momentum, gamma, beta, mean, invstd, scale, shift, running_mean, running_var,
+      ldp);
   HSP_LAUNCH_CHECK();
   if (dtype == HSP_DTYPE_BF16)
     bn_apply_kernel<__nv_bfloat16><<<grid, BN_THREADS, 0, st>>>(

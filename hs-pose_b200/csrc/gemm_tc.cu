@@ -52,7 +52,7 @@ struct Cfg {
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int PART_BYTES = 4 * BN * 2 * (int)sizeof(float);   // [row group][{sum,sq}][BN]
-  static constexpr int FIXED = 2 * OUT_STAGE_BYTES + PART_BYTES + BN * (int)sizeof(float) + 512 /*barriers*/ +
+  static constexpr int FIXED = 2 * OUT_STAGE_BYTES + PART_BYTES + 2 * BN * (int)sizeof(float) + 512 /*barriers*/ +
                                1024 /*alignment slack*/;
   static constexpr int STAGES_RAW = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -76,7 +76,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  // default (.release.cta) semantics: a cluster-scope release would drain this thread's in-flight TMA loads
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -225,8 +226,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   unsigned char* sB = sA + STAGES * C::A_BYTES;              // [STAGES][B_BYTES]
   unsigned char* sO = sB + STAGES * C::B_BYTES;              // [2][OUT_STAGE_BYTES]
   float* s_part = reinterpret_cast<float*>(sO + 2 * OUT_STAGE_BYTES);   // [4][2][BN]
-  float* s_bias = s_part + 4 * 2 * BN;                       // [BN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + BN);
+  float* s_bias = s_part + 4 * 2 * BN;                       // [2][BN] (double-buffered across tiles)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 2 * BN);
   uint64_t* full = bars;                                     // [STAGES]
   uint64_t* empty = bars + STAGES;                           // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;                       // [2] accumulator ready
@@ -357,6 +358,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = q * 32 + lane;                // accumulator row of this thread
     const int etid = tid - 64;                    // 0..127
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool do_stats = p.stats != nullptr && !OUT_F32;
+    constexpr int NV = OUT_COLS;                  // accumulator values per thread per chunk
+    auto load_bias = [&](int w, int slot) {       // bias slice of work item w -> s_bias[slot]
+      const int n0w = ((w / p.splits) % tiles_n) * BN;
+      for (int c = etid; c < BN; c += EPI_THREADS)
+        s_bias[slot * BN + c] = (p.bias && n0w + c < p.N) ? __ldg(p.bias + n0w + c) : 0.f;
+    };
+    auto load_acc = [&](uint32_t taddr, uint32_t* dst) {
+      tmem_ld32(taddr, *reinterpret_cast<uint32_t (*)[32]>(dst));
+      if (NV == 64) tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t (*)[32]>(dst + 32));
+    };
+    if (cluster_id < n_work) load_bias(cluster_id, 0);
     int it = 0;
     uint32_t ost = 0;                             // staging-buffer counter
     for (int w = cluster_id; w < n_work; w += n_clusters, ++it) {
@@ -365,27 +378,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int mblk = tm * CTAS + (int)rank;
       const int m0 = mblk * BM, n0 = tn * BN;
       const int buf = it & 1;
-      epi_barrier();                              // previous tile's s_bias / s_part readers are done
-      for (int c = etid; c < BN; c += EPI_THREADS) s_bias[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
+      epi_barrier();                              // s_bias[it & 1] written; previous tile's s_bias / s_part readers done
+      if (w + n_clusters < n_work) load_bias(w + n_clusters, (it + 1) & 1);
+      const float* bs_tile = s_bias + (it & 1) * BN;
       mbar_wait(tfull + buf, (it >> 1) & 1);
       tc_fence_after();
+      const bool full_rows = m0 + BM <= p.M;      // warp-uniform: only the last row block masks rows
       const bool row_ok = m0 + row < p.M;
-#pragma unroll 1
+      uint32_t v[2][NV];
+      load_acc(t_lane + (uint32_t)(buf * BN), v[0]);
+#pragma unroll
       for (int ch = 0; ch < CHUNKS; ++ch, ++ost) {
         unsigned char* so = sO + (ost & 1) * OUT_STAGE_BYTES;
-        if (etid == 0) tma_store_wait_read<1>();  // the store that last read this buffer has finished reading
-        epi_barrier();                            // ... and everyone knows (also orders the s_bias writes)
-        uint32_t v[OUT_F32 ? 32 : 64];
-        {
-          uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-          tmem_ld32(t_lane + (uint32_t)(buf * BN + ch * OUT_COLS), v0);
-          if (!OUT_F32) {
-            uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
-            tmem_ld32(t_lane + (uint32_t)(buf * BN + ch * OUT_COLS + 32), v1);
-          }
-          tmem_ld_wait();
-        }
-        if (ch == CHUNKS - 1) {                   // all TMEM reads of this accumulator are complete
+        uint32_t* vc = v[ch & 1];
+        tmem_ld_wait();                           // chunk ch is in registers
+        if (ch + 1 < CHUNKS) {
+          load_acc(t_lane + (uint32_t)(buf * BN + (ch + 1) * OUT_COLS), v[(ch + 1) & 1]);   // in flight during the conversion
+        } else {                                  // every TMEM read of this accumulator has completed
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -393,55 +402,71 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (p.debug & 1) continue;
+        if (!full_rows && !row_ok) {
+#pragma unroll
+          for (int e = 0; e < NV; ++e) vc[e] = 0u;
+        }
         // + bias, convert, write this thread's row into the 128-byte-swizzled staging tile
         unsigned char* srow = so + row * 128;
-        const float* bs = s_bias + ch * OUT_COLS;
+        const float4* bs4 = reinterpret_cast<const float4*>(bs_tile + ch * OUT_COLS);
+        const bool add_bias = p.bias != nullptr && (full_rows || row_ok);
         if (OUT_F32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {           // 8 x 16 bytes = 32 floats
-            float4 o;
-            o.x = row_ok ? __uint_as_float(v[4 * j + 0]) + bs[4 * j + 0] : 0.f;
-            o.y = row_ok ? __uint_as_float(v[4 * j + 1]) + bs[4 * j + 1] : 0.f;
-            o.z = row_ok ? __uint_as_float(v[4 * j + 2]) + bs[4 * j + 2] : 0.f;
-            o.w = row_ok ? __uint_as_float(v[4 * j + 3]) + bs[4 * j + 3] : 0.f;
+            float4 o = make_float4(__uint_as_float(vc[4 * j]), __uint_as_float(vc[4 * j + 1]),
+                                   __uint_as_float(vc[4 * j + 2]), __uint_as_float(vc[4 * j + 3]));
+            if (add_bias) {
+              const float4 b4 = bs4[j];
+              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            }
             *reinterpret_cast<float4*>(srow + ((j ^ (row & 7)) << 4)) = o;
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {           // 8 x 16 bytes = 64 bf16
-            uint4 o;
-            float f[8];
+            float2 f[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = row_ok ? __uint_as_float(v[8 * j + e]) + bs[8 * j + e] : 0.f;
-            o.x = pack_bf16(f[0], f[1]);
-            o.y = pack_bf16(f[2], f[3]);
-            o.z = pack_bf16(f[4], f[5]);
-            o.w = pack_bf16(f[6], f[7]);
+            for (int e = 0; e < 4; ++e)
+              f[e] = make_float2(__uint_as_float(vc[8 * j + 2 * e]), __uint_as_float(vc[8 * j + 2 * e + 1]));
+            if (add_bias) {
+              const float4 b0 = bs4[2 * j], b1 = bs4[2 * j + 1];
+              f[0] = __fadd2_rn(f[0], make_float2(b0.x, b0.y));
+              f[1] = __fadd2_rn(f[1], make_float2(b0.z, b0.w));
+              f[2] = __fadd2_rn(f[2], make_float2(b1.x, b1.y));
+              f[3] = __fadd2_rn(f[3], make_float2(b1.z, b1.w));
+            }
+            uint4 o;
+            o.x = pack_bf16(f[0].x, f[0].y);
+            o.y = pack_bf16(f[1].x, f[1].y);
+            o.z = pack_bf16(f[2].x, f[2].y);
+            o.w = pack_bf16(f[3].x, f[3].y);
             *reinterpret_cast<uint4*>(srow + ((j ^ (row & 7)) << 4)) = o;
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the TMA engine
+        // every earlier store has finished READING shared memory, in particular the one issued one chunk
+        // ago from the other staging buffer, which the next chunk overwrites after this barrier
+        if (etid == 0) tma_store_wait_read<0>();
         epi_barrier();
         if (etid == 0) tma_store_3d(&tmO, so, n0 + ch * OUT_COLS, m0, split);
-        if (p.stats && !OUT_F32) {
-          // column sums / sums of squares of the STORED bf16 values: lane = column pair, the warp's own
-          // 32 rows (written by this warp: the barrier above already ordered them)
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        if (do_stats) {
+          // column sums / sums of squares of the STORED bf16 values: lane = column pair, over the warp's own 32 rows
+          float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
 #pragma unroll 8
           for (int r = 0; r < 32; ++r) {
             const int rr = q * 32 + r;
             const uint32_t wv = *reinterpret_cast<const uint32_t*>(so + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) +
                                                                    ((lane & 3) << 2));
-            const float f0 = __uint_as_float(wv << 16), f1 = __uint_as_float(wv & 0xffff0000u);
-            s0 += f0; q0 = fmaf(f0, f0, q0);
-            s1 += f1; q1 = fmaf(f1, f1, q1);
+            const float2 f2 = make_float2(__uint_as_float(wv << 16), __uint_as_float(wv & 0xffff0000u));
+            s2 = __fadd2_rn(s2, f2);
+            q2 = __ffma2_rn(f2, f2, q2);
           }
           float* pp = s_part + (q * 2) * BN + ch * OUT_COLS + 2 * lane;
-          pp[0] = s0; pp[1] = s1;
-          pp[BN] = q0; pp[BN + 1] = q1;
+          *reinterpret_cast<float2*>(pp) = s2;
+          *reinterpret_cast<float2*>(pp + BN) = q2;
         }
       }
-      if (p.stats && !OUT_F32) {
+      if (do_stats) {
         epi_barrier();
         for (int c = etid; c < BN; c += EPI_THREADS) {
           if (n0 + c < p.N) {
@@ -546,18 +571,23 @@ extern "C" int hsp_gemm_debug(int flags) {
 }
 
 extern "C" int hsp_gemm_bf16_splits(int M, int N, int K, int out_f32) {
-  // split the reduction when the output has too few tiles to fill the SMs (wgrad: short, wide-K problems)
+  // Split the reduction when the output has too few tiles to fill the 74 CTA pairs, or when the tile count
+  // leaves the last wave mostly empty (wgrad: short, very deep problems).  Cost model: waves x k-blocks per
+  // work item (+ a per-item epilogue overhead); the smallest cost wins, ties go to fewer splits.
   using namespace hsp::gemm;
   if (!out_f32) return 1;
-  const int tiles = ((M + 255) / 256) * ((N + 255) / 256);
-  const int total_kb = (K + BK - 1) / BK;
-  int s = 74 / (tiles > 0 ? tiles : 1);
-  if (s < 1) s = 1;
-  if (s > 16) s = 16;
-  while (s > 1 && total_kb / s < 8) --s;
-  // every split must own at least one k-block
-  while (s > 1 && (s - 1) * ((total_kb + s - 1) / s) >= total_kb) --s;
-  return s;
+  const long tiles = (long)((M + 255) / 256) * ((N + 255) / 256);
+  const long total_kb = (K + BK - 1) / BK;
+  long best = -1;
+  int best_s = 1;
+  for (int s = 1; s <= 64; ++s) {
+    const long kb_per = (total_kb + s - 1) / s;
+    if (s > 1 && ((long)(s - 1) * kb_per >= total_kb || kb_per < 8)) continue;   // every split owns >= 8 k-blocks
+    const long waves = (tiles * s + 73) / 74;
+    const long cost = waves * (kb_per + 12);
+    if (best < 0 || cost < best) { best = cost; best_s = s; }
+  }
+  return best_s;
 }
 
 extern "C" int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M,

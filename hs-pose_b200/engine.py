@@ -9,14 +9,44 @@ permutations (still drawn by `torch.randperm` on the CPU generator, reference gc
 one graph launch.  Hand-written kernels enter the graph like any other launch (they run on
 `torch.cuda.current_stream()`); the NCCL all-reduce is captured too.
 """
+import contextlib
+import copy
+
 import torch
 
 from . import gcn3d, ops, parallel
 
+_RING = 4   # pinned staging slots per Pool_layer permutation (bounds how far the CPU may run ahead)
+
+
+class _PoolRows:
+    """Device buffer of one Pool_layer's sampled rows, fed from a small ring of pinned host buffers.
+    A slot is rewritten only after the event recorded behind its last H2D copy has completed, so a
+    copy still queued behind earlier graph replays never reads a permutation drawn for a later step."""
+
+    def __init__(self, vertice_num, pool_num, device):
+        self.vertice_num, self.pool_num = vertice_num, pool_num
+        self.dev = torch.empty(pool_num, dtype=torch.int32, device=device)
+        self.host = [torch.empty(pool_num, dtype=torch.int32).pin_memory() for _ in range(_RING)]
+        self.done = [None] * _RING
+        self.i = 0
+
+    def draw(self):
+        """torch.randperm on the CPU generator, exactly the reference's call (gcn3d.py:243)."""
+        k = self.i % _RING
+        self.i += 1
+        if self.done[k] is not None:
+            self.done[k].synchronize()
+        self.host[k].copy_(torch.randperm(self.vertice_num)[:self.pool_num])
+        self.dev.copy_(self.host[k], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.done[k] = ev
+
 
 class TrainStep:
     def __init__(self, model, lr=1e-4, clip=5.0, amp=True, graph=True, optimizer=None,
-                 tf32=True):
+                 tf32=False):
         self.model, self.clip, self.amp, self.use_graph = model, clip, amp, graph
         self.flat = parallel.FlatGradients(model.posenet.parameters())
         # default optimiser: Adam over ONE flat parameter (see FlatGradients.flatten_params)
@@ -28,34 +58,43 @@ class TrainStep:
         self.pool_rows = []          # static device buffers, one per Pool_layer call
         self._pool_call, self._draw_inline = 0, True
         self.launches_per_step = None
-        if tf32 and amp:
-            torch.backends.cuda.matmul.allow_tf32 = True   # fp32 leftovers (K=3 STE, per-object GEMVs)
+        self.tf32 = bool(tf32 and amp)   # opt-in, and scoped to the step body (never left set process-wide)
+        self._inputs_copied = None       # event behind the last H2D copy of a batch
 
     # ---- pooling permutations through static buffers
     def _provider(self, vertice_num, pool_num, device):
         i = self._pool_call
         self._pool_call += 1
         if i == len(self.pool_rows):
-            self.pool_rows.append((vertice_num, torch.empty(pool_num, dtype=torch.int32, device=device),
-                                   torch.empty(pool_num, dtype=torch.int32).pin_memory()))
-        vertice_num, dev_buf, host_buf = self.pool_rows[i]
+            self.pool_rows.append(_PoolRows(vertice_num, pool_num, device))
+        rows = self.pool_rows[i]
         if self._draw_inline:      # eager: draw at the point of use, exactly like the reference
-            host_buf.copy_(torch.randperm(vertice_num)[:pool_num])
-            dev_buf.copy_(host_buf, non_blocking=True)
-        return dev_buf
+            rows.draw()
+        return rows.dev
 
     def _refresh_pool_rows(self):
         """Graph mode: the draws of one forward, in forward order, before the replay."""
-        for vertice_num, dev_buf, host_buf in self.pool_rows:
-            host_buf.copy_(torch.randperm(vertice_num)[:host_buf.numel()])
-            dev_buf.copy_(host_buf, non_blocking=True)
+        for rows in self.pool_rows:
+            rows.draw()
+
+    @contextlib.contextmanager
+    def _tf32_scope(self):
+        if not self.tf32:
+            yield
+            return
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            yield
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
 
     # ---- the step itself
     def _body(self, batch, draw_inline):
         self._pool_call, self._draw_inline = 0, draw_inline
         prev = gcn3d.set_pool_rows_provider(self._provider)
         try:
-            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+            with self._tf32_scope(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
                 _, losses = self.model(**batch, do_loss=True)
             total = sum(v.reshape(()).float() for grp in losses.values() for v in grp.values())
             self.flat.zero()
@@ -73,6 +112,11 @@ class TrainStep:
         self.static_batch = {k: (torch.empty_like(v, device=dev) if torch.is_tensor(v) else v)
                              for k, v in batch.items()}
         self._load(batch)
+        # Warm-up (allocator, lazy optimiser state, cuBLAS/NCCL handles) WITHOUT side effects: parameters,
+        # optimiser state, BatchNorm buffers and both RNG streams are restored afterwards, so the first
+        # captured step is the first update the model sees — graph training follows the same trajectory
+        # as the eager loop (and as the reference's, engine/train.py:74-110).
+        snap = self._snapshot()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -80,17 +124,60 @@ class TrainStep:
                 self._body(self.static_batch, draw_inline=True)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self._refresh_pool_rows()
+        self._restore(snap)
         l0 = ops.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_loss = self._body(self.static_batch, draw_inline=False)
         self.launches_per_step = ops.launch_count() - l0
 
+    def _snapshot(self):
+        dev = next(self.model.parameters()).device
+        return {"params": [p.detach().clone() for p in self.model.parameters()],
+                "buffers": [b.detach().clone() for b in self.model.buffers()],
+                "opt": copy.deepcopy(self.opt.state_dict()),
+                "cpu_rng": torch.get_rng_state(), "cuda_rng": torch.cuda.get_rng_state(dev)}
+
+    def _restore(self, snap):
+        dev = next(self.model.parameters()).device
+        with torch.no_grad():
+            for p, q in zip(self.model.parameters(), snap["params"]):
+                p.copy_(q)
+            for b, q in zip(self.model.buffers(), snap["buffers"]):
+                b.copy_(q)
+            # optimiser state IN PLACE (the captured graph holds these tensors' addresses): a state that
+            # did not exist before the warm-up (first step) goes back to its initial value, zero
+            old = snap["opt"]["state"]
+            for idx, st in self.opt.state_dict()["state"].items():
+                live = self.opt.state[self._opt_param(idx)]
+                for name, val in live.items():
+                    if torch.is_tensor(val):
+                        if idx in old and name in old[idx]:
+                            val.copy_(old[idx][name])
+                        else:
+                            val.zero_()
+            self.flat.zero()
+        torch.set_rng_state(snap["cpu_rng"])
+        torch.cuda.set_rng_state(snap["cuda_rng"], dev)
+
+    def _opt_param(self, idx):
+        flat = [p for g in self.opt.param_groups for p in g["params"]]
+        return flat[idx]
+
     def _load(self, batch):
+        """H2D (or D2D) copies of the step's inputs into the static buffers.  The copies are
+        asynchronous: a caller that REWRITES its pinned host tensors between steps must call
+        `wait_inputs()` first (or hand in fresh tensors); reusing them unchanged needs nothing."""
         for k, v in batch.items():
             if torch.is_tensor(v):
                 self.static_batch[k].copy_(v, non_blocking=True)
+        self._inputs_copied = torch.cuda.Event()
+        self._inputs_copied.record()
+
+    def wait_inputs(self):
+        """Block until the last batch handed to __call__ has been copied off the host."""
+        if self._inputs_copied is not None:
+            self._inputs_copied.synchronize()
 
     def __call__(self, batch):
         """One train step.  `batch`: dict of HSPose.forward kwargs (host pinned or device

@@ -17,7 +17,7 @@ F32, BF16 = 0, 1   # HSP_DTYPE_*
 _launches = 0  # number of CUDA kernels launched through the C ABI (bench.py reads this)
 
 # kernels launched per entry point (memsets not counted)
-_KERNELS_PER_CALL = {"hsp_knn_feat": 2, "hsp_surface_conv_bwd": 2, "hsp_graph_conv_bwd": 2,
+_KERNELS_PER_CALL = {"hsp_losses_fwd": 2, "hsp_losses_bwd": 2, "hsp_bn_apply_fwd": 2, "hsp_knn_feat": 2, "hsp_surface_conv_bwd": 2, "hsp_graph_conv_bwd": 2,
                      "hsp_orl_global_fwd": 2, "hsp_chamfer_fwd": 2, "hsp_chamfer_bwd": 2,
                      "hsp_bn_relu_fwd": 3, "hsp_bn_relu_bwd": 3}
 
@@ -235,30 +235,29 @@ class _HSConvMixed(torch.autograd.Function):
         dirn = _need(dirn, torch.float32, "dirn")
         fm = _need(fm, torch.float32, "feature_map")
         B, N, Cin = fm.shape
-        with torch.autocast("cuda", enabled=False):
-            P = torch.addmm(bias.to(torch.bfloat16), fm.reshape(B * N, Cin).to(torch.bfloat16),
-                            W.to(torch.bfloat16)).view(B, N, (S + 1) * C)
+        fm16 = fm.reshape(B * N, Cin).to(torch.bfloat16)
+        W16 = W.to(torch.bfloat16)                       # (Cin, (S+1)C): read MN-major as the B operand
+        P = gemm_bf16(fm16, W16, b_mn=True, bias=bias).view(B, N, (S + 1) * C)
         need_grad = any(ctx.needs_input_grad)
         out, am = _graph_conv_fwd_raw(xyz, idx32, dirn, P, S, C, need_grad)
         if need_grad:
-            ctx.save_for_backward(xyz, idx32, dirn, P, am, fm, W)
+            ctx.save_for_backward(xyz, idx32, dirn, P, am, fm16, W16)
         ctx.dims = (S, C)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        xyz, idx32, dirn, P, am, fm, W = ctx.saved_tensors
+        xyz, idx32, dirn, P, am, fm16, W16 = ctx.saved_tensors
         S, C = ctx.dims
-        B, N, Cin = fm.shape
+        B, N = idx32.shape[0], idx32.shape[1]
+        Cin = fm16.shape[1]
         gout = _need(gout.float(), torch.float32, "gout")
         gP, gdirn, gb = _graph_conv_bwd_raw(xyz, idx32, dirn, P, am, gout, S, C, want_gbias=True)
-        # weight / input gradients as bf16 tensor-core GEMMs (fp32 accumulate): one cast pass over gP,
-        # then both GEMMs read half the bytes and run on the tcgen05 library kernels
+        # weight / input gradients on the K6 kernel (bf16 operands, fp32 accumulate): one cast pass over gP
         gP16 = gP.view(B * N, (S + 1) * C).to(torch.bfloat16)
-        with torch.autocast("cuda", enabled=False):
-            W16 = W.to(torch.bfloat16)
-            gfm = (gP16 @ W16.t()).view(B, N, Cin).float() if ctx.needs_input_grad[3] else None
-            gW = (fm.reshape(B * N, Cin).to(torch.bfloat16).t() @ gP16).float()
+        gfm = gemm_bf16(gP16, W16).view(B, N, Cin).float() if ctx.needs_input_grad[3] else None
+        gW = gemm_bf16(fm16, gP16, a_mn=True, b_mn=True, out_dtype=torch.float32,
+                       splits=gemm_splits(Cin, (S + 1) * C, B * N))
         return None, None, gdirn, gfm, gW, gb, None, None
 
 
@@ -588,7 +587,20 @@ def _bn_fwd_raw(x, gamma, beta, running_mean, running_var, eps, momentum, relu):
     return y, stats
 
 
-def _bn_bwd_raw(x, dy, gamma, beta, stats, relu, want_colsum):
+def _bn_fwd_from_partials(x, partials, gamma, beta, running_mean, running_var, eps, momentum, relu):
+    """Same as _bn_fwd_raw with the statistics partials (nblocks,2,C | row pitch ldp) from the GEMM epilogue."""
+    M, C = x.shape
+    dt = BF16 if x.dtype == torch.bfloat16 else F32
+    with torch.cuda.device(x.device):
+        y = torch.empty(M, C, dtype=x.dtype, device=x.device)
+        stats = torch.empty(4, C, dtype=torch.float32, device=x.device)
+        _call("hsp_bn_apply_fwd", _p(x), x.stride(0), M, C, dt, _p(partials), partials.shape[0],
+              partials.stride(1), _p(gamma), _p(beta), float(eps), float(momentum), int(relu),
+              _p(running_mean), _p(running_var), _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(y), C, _stream())
+    return y, stats
+
+
+def _bn_bwd_raw(x, dy, gamma, beta, stats, relu, want_colsum, dx_out=None):
     """-> (dx, dgamma, dbeta, colsum(dx) | None)."""
     M, C = x.shape
     dt = BF16 if x.dtype == torch.bfloat16 else F32
@@ -597,11 +609,11 @@ def _bn_bwd_raw(x, dy, gamma, beta, stats, relu, want_colsum):
         dy = dy.contiguous()
     lib = _lib.load()
     with torch.cuda.device(x.device):
-        dx = torch.empty(M, C, dtype=x.dtype, device=x.device)
+        dx = torch.empty(M, C, dtype=x.dtype, device=x.device) if dx_out is None else dx_out
         dgb = torch.empty(3, C, dtype=torch.float32, device=x.device)
         ws = _workspace(lib.hsp_bn_workspace_bytes(M, C), x.device)
         _call("hsp_bn_relu_bwd", _p(x), x.stride(0), _p(dy), dy.stride(0), M, C, dt, _p(gamma),
-              _p(beta), _p(stats[0]), _p(stats[1]), int(relu), _p(dgb[0]), _p(dgb[1]), _p(dx), C,
+              _p(beta), _p(stats[0]), _p(stats[1]), int(relu), _p(dgb[0]), _p(dgb[1]), _p(dx), dx.stride(0),
               _p(dgb[2]) if want_colsum else None, _p(ws), ws.numel(), _stream())
     if want_colsum:
         global _launches
@@ -617,18 +629,18 @@ def bn_relu(x, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, r
 class _LinearBnRelu(torch.autograd.Function):
     """z = relu?(batchnorm_train(x @ W^T + b)) over the rows of x (M,K) — one Conv1d(k=1) ->
     BatchNorm1d -> ReLU block of the dense per-point MLPs (reference FaceRecon.py:38-68,
-    PoseR.py:26-29, PoseTs.py:31-34) as ONE autograd node on the mixed-precision path:
-    bf16 tensor-core GEMMs (library), K6b for the BN, and the Linear's bias gradient comes out
-    of the BN-backward kernel (column sums of dY) instead of a separate reduction pass."""
+    PoseR.py:26-29, PoseTs.py:31-34) as ONE autograd node on the mixed-precision path: the K6
+    tensor-core GEMM emits the BatchNorm statistics in its epilogue (no stand-alone reduction pass),
+    K6b normalises; backward = K6b + the K6 dgrad / wgrad GEMMs; the Linear's bias gradient comes
+    out of the BN-backward kernel (column sums of dY)."""
 
     @staticmethod
     def forward(ctx, x, W, b, gamma, beta, running_mean, running_var, eps, momentum, relu):
-        xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
-        Wb = W.to(torch.bfloat16)
-        with torch.autocast("cuda", enabled=False):
-            y = torch.addmm(b.to(torch.bfloat16), xb, Wb.t()) if b is not None else xb @ Wb.t()
+        xb = _as_gemm_operand(x)
+        Wb = _as_gemm_operand(W)
+        y, part = gemm_bf16(xb, Wb, bias=b, stats=True)
         g32, b32 = gamma.float().contiguous(), beta.float().contiguous()
-        z, stats = _bn_fwd_raw(y, g32, b32, running_mean, running_var, eps, momentum, relu)
+        z, stats = _bn_fwd_from_partials(y, part, g32, b32, running_mean, running_var, eps, momentum, relu)
         ctx.save_for_backward(xb, Wb, y, g32, b32, stats)
         ctx.relu, ctx.has_bias = int(relu), b is not None
         return z
@@ -637,9 +649,8 @@ class _LinearBnRelu(torch.autograd.Function):
     def backward(ctx, dz):
         xb, Wb, y, g32, b32, stats = ctx.saved_tensors
         dy, dgamma, dbeta, colsum = _bn_bwd_raw(y, dz, g32, b32, stats, ctx.relu, ctx.has_bias)
-        with torch.autocast("cuda", enabled=False):
-            dx = dy @ Wb if ctx.needs_input_grad[0] else None
-            dW = (dy.t() @ xb).float()
+        dx = gemm_bf16(dy, Wb, b_mn=True) if ctx.needs_input_grad[0] else None
+        dW = _wgrad(dy, xb)
         return dx, dW, colsum, dgamma, dbeta, None, None, None, None, None
 
 
@@ -651,27 +662,35 @@ def linear_bn_relu(x, W, b, gamma, beta, running_mean, running_var, eps=1e-5, mo
 class _MultiLinearBnRelu(torch.autograd.Function):
     """Several Conv1d(k=1) -> BatchNorm1d -> ReLU blocks that read the SAME (M,K) input (the
     1286-channel feature buffer feeds rot_green.conv1, rot_red.conv1, ts.conv1 and
-    conv1d_block[0]: reference PoseNet9D.py:37-50, FaceRecon.py:114-116) as one autograd node.
-    The input gradient is accumulated inside the dgrad GEMMs (beta = 1) instead of by separate
-    full-size add passes."""
+    conv1d_block[0]: reference PoseNet9D.py:37-50, FaceRecon.py:114-116) as one autograd node and
+    ONE K6 GEMM each way: the weights are concatenated along the output axis, so the input is read
+    from HBM once in the forward, the input gradient is a single dgrad over the concatenated dY
+    (accumulated in TMEM instead of read-modify-write passes) and the weight gradients a single wgrad."""
 
     @staticmethod
     def forward(ctx, x, buffers, *params):
         # params: (W, b, gamma, beta) per block; buffers: [(running_mean, running_var, eps, momentum, relu)]
-        xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+        xb = _as_gemm_operand(x)
         n = len(buffers)
-        saved, outs, meta = [xb], [], []
+        Ws = [params[4 * i] for i in range(n)]
+        widths = [W.shape[0] for W in Ws]
+        tot = sum(widths)
+        Wcat = torch.cat(Ws, dim=0).to(torch.bfloat16)                       # (sum N_i, K)
+        has_bias = [params[4 * i + 1] is not None for i in range(n)]
+        bcat = torch.cat([params[4 * i + 1].float() if has_bias[i] else
+                          torch.zeros(widths[i], dtype=torch.float32, device=x.device) for i in range(n)])
+        ycat, part = gemm_bf16(xb, Wcat, bias=bcat, stats=True)              # (M, tot), (M/128, 2, tot)
+        saved, outs, meta, off = [xb, Wcat, ycat], [], [], 0
         for i in range(n):
-            W, b, gamma, beta = params[4 * i:4 * i + 4]
+            gamma, beta = params[4 * i + 2], params[4 * i + 3]
             rm, rv, eps, mom, relu = buffers[i]
-            Wb = W.to(torch.bfloat16)
-            with torch.autocast("cuda", enabled=False):
-                y = torch.addmm(b.to(torch.bfloat16), xb, Wb.t()) if b is not None else xb @ Wb.t()
             g32, b32 = gamma.float().contiguous(), beta.float().contiguous()
-            z, stats = _bn_fwd_raw(y, g32, b32, rm, rv, eps, mom, relu)
-            saved += [Wb, y, g32, b32, stats]
-            meta.append((int(relu), b is not None))
+            z, stats = _bn_fwd_from_partials(ycat[:, off:off + widths[i]], part[:, :, off:off + widths[i]],
+                                             g32, b32, rm, rv, eps, mom, relu)
+            saved += [g32, b32, stats]
+            meta.append((int(relu), has_bias[i], off, widths[i]))
             outs.append(z)
+            off += widths[i]
         ctx.save_for_backward(*saved)
         ctx.meta = meta
         return tuple(outs)
@@ -679,21 +698,26 @@ class _MultiLinearBnRelu(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *dzs):
         saved = ctx.saved_tensors
-        xb = saved[0]
-        grads, dx = [], None
-        for i, (relu, has_bias) in enumerate(ctx.meta):
-            Wb, y, g32, b32, stats = saved[1 + 5 * i:6 + 5 * i]
+        xb, Wcat, ycat = saved[:3]
+        M, tot = ycat.shape
+        dycat = torch.empty_like(ycat)
+        grads = []
+        for i, (relu, has_bias, off, wd) in enumerate(ctx.meta):
+            g32, b32, stats = saved[3 + 3 * i:6 + 3 * i]
             dz = dzs[i]
             if dz is None:
-                grads += [None, None, None, None]
+                dycat[:, off:off + wd].zero_()
+                grads.append((None, None, None))
                 continue
-            dy, dgamma, dbeta, colsum = _bn_bwd_raw(y, dz, g32, b32, stats, relu, has_bias)
-            with torch.autocast("cuda", enabled=False):
-                if ctx.needs_input_grad[0]:
-                    dx = dy @ Wb if dx is None else dx.addmm_(dy, Wb)
-                dW = (dy.t() @ xb).float()
-            grads += [dW, colsum, dgamma, dbeta]
-        return (dx, None, *grads)
+            _, dgamma, dbeta, colsum = _bn_bwd_raw(ycat[:, off:off + wd], dz, g32, b32, stats, relu, has_bias,
+                                                   dx_out=dycat[:, off:off + wd])
+            grads.append((colsum, dgamma, dbeta))
+        dx = gemm_bf16(dycat, Wcat, b_mn=True) if ctx.needs_input_grad[0] else None
+        dWcat = _wgrad(dycat, xb)                                            # (tot, K) fp32
+        out = []
+        for (relu, has_bias, off, wd), (colsum, dgamma, dbeta) in zip(ctx.meta, grads):
+            out += [dWcat[off:off + wd] if dgamma is not None else None, colsum, dgamma, dbeta]
+        return (dx, None, *out)
 
 
 def multi_linear_bn_relu(x, blocks):
@@ -746,6 +770,116 @@ def gemm_bf16(a, b, a_mn=False, b_mn=False, bias=None, out=None, out_dtype=torch
     if out is None and res.shape[-1] != N:
         res = res[..., :N]
     return (res, st) if stats else res
+
+
+def _as_gemm_operand(t):
+    """bf16 2-D matrix whose row pitch is 16-byte aligned (TMA requirement); pads columns if needed."""
+    if t.dtype != torch.bfloat16:
+        t = t.to(torch.bfloat16)
+    if t.stride(-1) != 1 or (t.stride(0) * 2) % 16 != 0 or t.data_ptr() % 16 != 0:
+        cols = t.shape[1]
+        buf = torch.zeros(t.shape[0], cols + ((-cols) % 8), dtype=torch.bfloat16, device=t.device)
+        buf[:, :cols] = t
+        t = buf[:, :cols]
+    return t
+
+
+def _wgrad(dy, x):
+    """dW (N,K) fp32 = dy^T (M,N) . x (M,K): both operands read MN-major, split-K, planes added in order."""
+    M, N = dy.shape
+    K = x.shape[1]
+    return gemm_bf16(dy, x, a_mn=True, b_mn=True, out_dtype=torch.float32, splits=gemm_splits(N, K, M))
+
+
+class _LinearTC(torch.autograd.Function):
+    """y (M,N) bf16 = x (M,K) . W (N,K)^T + b on the K6 kernel, forward / dgrad / wgrad (no library GEMM)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        xb = _as_gemm_operand(x)
+        Wb = _as_gemm_operand(W)
+        y = gemm_bf16(xb, Wb, bias=b)
+        ctx.save_for_backward(xb, Wb)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, Wb = ctx.saved_tensors
+        dyb = _as_gemm_operand(dy)
+        dx = gemm_bf16(dyb, Wb, b_mn=True) if ctx.needs_input_grad[0] else None
+        dW = _wgrad(dyb, xb) if ctx.needs_input_grad[1] else None
+        db = dyb.float().sum(dim=0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dW, db
+
+
+def linear_tc(x, W, b=None):
+    """F.linear on the tensor-core kernel: x (..., K), W (N, K) -> (..., N) bf16.  K % 8 == 0."""
+    shape = x.shape
+    y = _LinearTC.apply(x.reshape(-1, shape[-1]), W, b)
+    return y.view(*shape[:-1], W.shape[0])
+
+
+# ------------------------------------------------------------ K8: fused loss graph
+LOSS_TERMS = ("Rot1", "Rot1_cos", "Rot2", "Rot2_cos", "Rot_r_a", "Tran", "Size", "R_con",
+              "recon_per_p", "recon_p_f", "recon_point_vote", "recon_point_r", "recon_point_t", "recon_point_s",
+              "recon_point_self", "geo_point", "Prop_pm", "Prop_sym_recon", "Prop_sym_rt")
+LOSS_WEIGHT_FLAGS = ("rot_1_w", "rot_2_w", "rot_regular", "tran_w", "size_w", "r_con_w", "recon_n_w", "recon_d_w",
+                     "recon_f_w", "recon_v_w", "recon_bb_r_w", "recon_bb_t_w", "recon_bb_s_w", "recon_bb_self_w",
+                     "geo_p_w", "prop_pm_w", "prop_sym_w")
+
+
+class _FusedLosses(torch.autograd.Function):
+    """All 19 loss terms of stage 'PoseNet_only' (K8): two launches forward, two backward."""
+
+    @staticmethod
+    def forward(ctx, weights, face, recon, p_green, p_red, f_green, f_red, pred_T, pred_s, PC, gt_R, gt_t, gt_s,
+                mean_shape, sym, obj_id):
+        face = _need(face, torch.float32, "face")
+        recon = _need(recon, torch.float32, "recon")
+        PC = _need(PC, torch.float32, "PC")
+        B, N, _ = PC.shape
+        if face.shape != (B, N, 30) or recon.shape != (B, N, 3):
+            raise ValueError("fused_losses: face (B,N,30), recon (B,N,3), PC (B,N,3)")
+        pred = torch.cat([p_green.float(), p_red.float(), f_green.float().view(B, 1), f_red.float().view(B, 1),
+                          pred_T.float(), pred_s.float()], dim=1).contiguous()
+        gt = torch.cat([gt_R.float().reshape(B, 9), gt_t.float(), gt_s.float(), mean_shape.float(), sym.float(),
+                        obj_id.float().view(B, 1)], dim=1).contiguous()
+        lib = _lib.load()
+        nt, ns = lib.hsp_losses_num_terms(), lib.hsp_losses_num_sums()
+        w = (ctypes.c_float * len(weights))(*weights)
+        with torch.cuda.device(PC.device):
+            sums = torch.empty(B, ns, dtype=torch.float32, device=PC.device)
+            pieces = torch.empty(B, nt, dtype=torch.float32, device=PC.device)
+            _call("hsp_losses_fwd", _p(face), _p(recon), _p(PC), _p(pred), _p(gt), w, B, N, _p(sums), _p(pieces),
+                  _stream())
+        ctx.save_for_backward(face, recon, PC, pred, gt, sums)
+        ctx.weights = tuple(weights)
+        return pieces.sum(dim=0)
+
+    @staticmethod
+    def backward(ctx, gterm):
+        face, recon, PC, pred, gt, sums = ctx.saved_tensors
+        B, N, _ = PC.shape
+        gterm = _need(gterm.float(), torch.float32, "gterm")
+        w = (ctypes.c_float * len(ctx.weights))(*ctx.weights)
+        with torch.cuda.device(PC.device):
+            gface = torch.empty_like(face)
+            grecon = torch.empty_like(recon)
+            gpred = torch.empty_like(pred)
+            ws = torch.empty(B, 54, dtype=torch.float32, device=PC.device)
+            _call("hsp_losses_bwd", _p(face), _p(recon), _p(PC), _p(pred), _p(gt), w, _p(sums), _p(gterm), B, N,
+                  _p(gface), _p(grecon), _p(gpred), _p(ws), _stream())
+        return (None, gface, grecon, gpred[:, 0:3], gpred[:, 3:6], gpred[:, 6], gpred[:, 7], gpred[:, 8:11],
+                gpred[:, 11:14], None, None, None, None, None, None, None)
+
+
+def fused_losses(weights, face, recon, p_green, p_red, f_green, f_red, pred_T, pred_s, PC, gt_R, gt_t, gt_s,
+                 mean_shape, sym, obj_id):
+    """K8 -> dict {term name: scalar} over LOSS_TERMS.  `weights`: the 17 floats of LOSS_WEIGHT_FLAGS."""
+    terms = _FusedLosses.apply(tuple(float(x) for x in weights), face, recon, p_green, p_red, f_green, f_red,
+                               pred_T, pred_s, PC, gt_R, gt_t, gt_s, mean_shape, sym, obj_id)
+    return {name: terms[i] for i, name in enumerate(LOSS_TERMS)}
 
 
 # ---------------------------------------------------------------- chamfer

@@ -59,6 +59,41 @@ def synth_batch(B, N=1028, seed=1, train=True):
     return out
 
 
+def synth_predictions(B, N, seed):
+    """Random but plausible network outputs + ground truth for the loss goldens (all six
+    categories present so every symmetry branch of the losses runs)."""
+    g = torch.Generator().manual_seed(seed)
+    cat = torch.arange(B) % 6
+    R = random_rotations(B, g)
+    t = torch.tensor([0.0, 0.0, 0.8]).repeat(B, 1) + torch.randn(B, 3, generator=g) * 0.02
+    s = torch.randn(B, 3, generator=g) * 0.01
+    ms = _MEAN_SHAPE[cat].clone()
+    obj = (torch.rand(B, N, 3, generator=g) - 0.5) * (ms + s).unsqueeze(1)        # points inside the box
+    PC = obj @ R.transpose(1, 2) + t.unsqueeze(1)
+    nrm = lambda v: v / v.norm(dim=-1, keepdim=True)
+    gt_axes = R.transpose(1, 2)                                                    # (B,3,3): axes[f] = R[:, f]
+    face_axes = torch.cat([gt_axes[:, [1, 0, 2]], -gt_axes[:, [1, 2, 0]]], dim=1)  # network order y+,x+,z+,y-,z-,x-
+    half = ((ms + s) / 2.0)
+    d_plus, d_minus = half.unsqueeze(1) - obj, half.unsqueeze(1) + obj             # (B,N,3) for x,y,z
+    face_d = torch.stack([d_plus[..., 1], d_plus[..., 0], d_plus[..., 2], d_minus[..., 1], d_minus[..., 2],
+                          d_minus[..., 0]], dim=-1)
+    pred = {
+        "face_normal": nrm(face_axes.unsqueeze(1) + 0.15 * torch.randn(B, N, 6, 3, generator=g)),
+        "face_dis": face_d + 0.01 * torch.randn(B, N, 6, generator=g),
+        "face_f": torch.rand(B, N, 6, generator=g) * 0.9 + 0.05,
+        "recon": PC + 0.01 * torch.randn(B, N, 3, generator=g),
+        "p_green_R": nrm(R[:, :, 1] + 0.2 * torch.randn(B, 3, generator=g)),
+        "p_red_R": nrm(R[:, :, 0] + 0.2 * torch.randn(B, 3, generator=g)),
+        "f_green_R": torch.rand(B, generator=g) * 0.8 + 0.1,
+        "f_red_R": torch.rand(B, generator=g) * 0.8 + 0.1,
+        "Pred_T": t + 0.01 * torch.randn(B, 3, generator=g),
+        "Pred_s": s + 0.005 * torch.randn(B, 3, generator=g),
+    }
+    gt = {"PC": PC, "gt_R": R, "gt_t": t, "gt_s": s, "mean_shape": ms, "sym": _SYM[cat].clone(),
+          "obj_id": cat.float()}
+    return pred, gt
+
+
 def tiled_cloud(B, N=1028, unique=400, seed=7):
     """Stress set: `unique` points tiled to N (exact duplicates / distance ties)."""
     g = torch.Generator().manual_seed(seed)

@@ -234,9 +234,10 @@ int hsp_bn_relu_bwd(const void* x, int ldx, const void* dy, int lddy, int M, int
                     void* stream);
 
 /* Forward with the statistics partials already produced by hsp_gemm_bf16's epilogue: `partials`
- * is (nblocks, 2, C) column sums / sums of squares over disjoint row blocks covering the M rows. */
+ * is (nblocks, 2, C) column sums / sums of squares over disjoint row blocks covering the M rows,
+ * row pitch ldp >= C floats (a column slice of a wider partial matrix).                           */
 int hsp_bn_apply_fwd(const void* x, int ldx, int M, int C, int dtype, const float* partials,
-                     int nblocks, const float* gamma, const float* beta, float eps, float momentum,
+                     int nblocks, int ldp, const float* gamma, const float* beta, float eps, float momentum,
                      int relu, float* running_mean, float* running_var, float* mean, float* invstd,
                      float* scale_shift, void* y, int ldy, void* stream);
 
@@ -268,6 +269,32 @@ int hsp_gemm_debug(int flags);
 int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major,
                   int M, int N, int K, const float* bias, void* out, int ldo, int out_f32,
                   int splits, float* stats, int tile_n, int ctas, void* stream);
+
+/* ------------------------------------------------------------------ K8 ---
+ * The 19-term loss graph of training stage 'PoseNet_only' (L1 loss type), forward and backward:
+ *   losses/fs_net_loss.py:31-76 (Rot1, Rot1_cos, Rot2, Rot2_cos, Rot_r_a, Tran, Size, R_con)
+ *   losses/recon_loss.py:464-649 (recon_per_p, recon_p_f, recon_point_vote/_r/_t/_s/_self)
+ *   losses/geometry_loss.py:123-150 (geo_point), losses/prop_loss.py:156-277 (Prop_pm, Prop_sym_recon/_rt)
+ * incl. the face normalisation / sigmoid of PoseNet9D.py:28-33 and tools/plane_utils.py:24-48.
+ *   face (B,N,30) raw face-head output, recon (B,N,3), PC (B,N,3);
+ *   pred (B,14) = [p_green 3 | p_red 3 | f_green | f_red | Pred_T 3 | Pred_s 3];
+ *   gt   (B,23) = [gt_R 9 row-major | gt_t 3 | gt_s 3 | mean_shape 3 | sym 4 | obj_id];
+ *   weights: HOST array of 17 floats (rot_1_w, rot_2_w, rot_regular, tran_w, size_w, r_con_w, recon_n_w,
+ *            recon_d_w, recon_f_w, recon_v_w, recon_bb_r_w, recon_bb_t_w, recon_bb_s_w, recon_bb_self_w,
+ *            geo_p_w, prop_pm_w, prop_sym_w of config/config.py).
+ * fwd: sums (B, hsp_losses_num_sums()) per-object sums kept for the backward; pieces (B, 19) per-object
+ *      contributions — term k = sum_b pieces[b,k] (order: the list above).
+ * bwd: gterm (19) upstream gradient per term -> gface (B,N,30), grecon (B,N,3), gpred (B,14);
+ *      gmom_ws: B*54 floats of scratch.  Deterministic.                                          */
+int hsp_losses_num_terms(void);
+int hsp_losses_num_sums(void);
+int hsp_losses_fwd(const float* face, const float* recon, const float* PC, const float* pred,
+                   const float* gt, const float* weights, int B, int N, float* sums, float* pieces,
+                   void* stream);
+int hsp_losses_bwd(const float* face, const float* recon, const float* PC, const float* pred,
+                   const float* gt, const float* weights, const float* sums, const float* gterm,
+                   int B, int N, float* gface, float* grecon, float* gpred, float* gmom_ws,
+                   void* stream);
 
 #ifdef __cplusplus
 }

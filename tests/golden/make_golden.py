@@ -279,11 +279,62 @@ def golden_augment(FLAGS):
     save("aug", **arrays)
 
 
+def golden_losses(FLAGS):
+    """The reference's recon_6face / geo / prop loss modules (losses/*.py) on synthetic
+    predictions: every term and the gradient of each group's sum w.r.t. every prediction."""
+    from losses.geometry_loss import geo_transform_loss
+    from losses.prop_loss import prop_rot_loss
+    from losses.recon_loss import recon_6face_loss
+    from tools.geom_utils import generate_RT
+    sys.path.insert(0, ROOT)
+    from hspose_b200.synth import synth_predictions
+    pred, gt = synth_predictions(12, 257, seed=11)
+    leaves = {k: v.clone().requires_grad_() for k, v in pred.items()}
+    arrays = {}
+    groups = {
+        "recon": lambda p: recon_6face_loss()(
+            ['Per_point', 'Point_voting'],
+            {'F_n': p["face_normal"], 'F_d': p["face_dis"], 'F_c': p["face_f"], 'Rot1': p["p_green_R"],
+             'Rot1_f': p["f_green_R"].detach(), 'Rot2': p["p_red_R"], 'Rot2_f': p["f_red_R"].detach(),
+             'Tran': p["Pred_T"], 'Size': p["Pred_s"]},
+            {'R': gt["gt_R"], 'T': gt["gt_t"], 'Size': gt["gt_s"], 'Mean_shape': gt["mean_shape"],
+             'Points': gt["PC"]}, gt["sym"], gt["obj_id"]),
+        "geo": lambda p: geo_transform_loss()(
+            ['Geo_point'],
+            {'Rot1': p["p_green_R"], 'Rot2': p["p_red_R"], 'Tran': p["Pred_T"], 'Size': p["Pred_s"],
+             'Rot1_f': p["f_green_R"].detach(), 'Rot2_f': p["f_red_R"].detach()},
+            {'Points': gt["PC"], 'R': gt["gt_R"], 'T': gt["gt_t"], 'Mean_shape': gt["mean_shape"]}, gt["sym"]),
+        "prop": lambda p: prop_rot_loss()(
+            ['Prop_pm', 'Prop_sym'],
+            {'Recon': p["recon"], 'Rot1': p["p_green_R"], 'Rot2': p["p_red_R"], 'Tran': p["Pred_T"],
+             'Scale': p["Pred_s"], 'Rot1_f': p["f_green_R"].detach(), 'Rot2_f': p["f_red_R"].detach()},
+            {'Points': gt["PC"], 'R': gt["gt_R"], 'T': gt["gt_t"], 'Mean_shape': gt["mean_shape"]}, gt["sym"]),
+    }
+    for gname, fn in groups.items():
+        for v in leaves.values():
+            v.grad = None
+        terms = fn(leaves)
+        total = 0.0
+        for k, v in terms.items():
+            if torch.is_tensor(v):
+                arrays[f"{gname}::{k}"] = v.detach().reshape(())
+                total = total + v
+        total.backward()
+        for k, v in leaves.items():
+            if v.grad is not None and float(v.grad.abs().max()) > 0:
+                arrays[f"{gname}::grad::{k}"] = v.grad.clone()
+    # evaluation post-processing (tools/geom_utils.py:232-244)
+    with torch.no_grad():
+        arrays["generate_RT"] = generate_RT([pred["p_green_R"], pred["p_red_R"]],
+                                            [pred["f_green_R"], pred["f_red_R"]], pred["Pred_T"], "vec", gt["sym"])
+    save("losses", **arrays)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     _args = sys.argv[1:]
     FLAGS, gcn3d = import_reference()
-    which = _args or ["knn", "ops", "e2e_eval", "e2e_train", "aug"]
+    which = _args or ["knn", "ops", "e2e_eval", "e2e_train", "aug", "losses"]
     if "knn" in which:
         golden_knn(gcn3d)
     if "ops" in which:
@@ -294,3 +345,5 @@ if __name__ == "__main__":
         golden_e2e_train(FLAGS, gcn3d)
     if "aug" in which:
         golden_augment(FLAGS)
+    if "losses" in which:
+        golden_losses(FLAGS)

@@ -268,10 +268,14 @@ def test_api_functions_match_oracle(cuda):
     np.testing.assert_allclose(G[:, 0].cpu().numpy(), co.orl_global_fwd(feat.numpy(), idx.cpu().numpy()), atol=1e-5)
 
 
-def test_mixed_precision_step_close_to_fp32(cuda):
+@pytest.mark.parametrize("groups,dense_bar", [(("fsnet",), 0.97), (("fsnet", "recon", "geo", "prop"), 0.80)])
+def test_mixed_precision_step_close_to_fp32(cuda, groups, dense_bar):
     """bf16 fast path (autocast) vs the fp32 path of the same module on the same batch, with
     the fp32 run's RF-F neighbour tables forced into the bf16 run (removes the KNN
-    discontinuity): losses within bf16 tolerance, gradients with high cosine similarity."""
+    discontinuity): losses within bf16 tolerance, gradients with high cosine similarity.
+    With the recon_6face voting terms in the objective the dense-path gradient also carries the
+    weighted plane fit (a 3x3 inverse of sums over 1028 points: ill-conditioned in fp32 already,
+    tests/test_losses_cpu.py), so bf16 activations move it more (measured cosine 0.89)."""
     from hspose_b200 import gcn3d
     from hspose_b200.HSPose import HSPose
     rf = []
@@ -283,7 +287,7 @@ def test_mixed_precision_step_close_to_fp32(cuda):
         res = {}
         for mode in ("fp32", "bf16"):
             F.train, F.gcn_n_num = 1, 20
-            net = fill_params(HSPose("PoseNet_only", chamfer_w=1.0)).to(cuda).train()
+            net = fill_params(HSPose("PoseNet_only", chamfer_w=1.0, loss_groups=groups)).to(cuda).train()
             for m in net.modules():
                 if isinstance(m, torch.nn.Dropout):
                     m.p = 0.0
@@ -307,7 +311,7 @@ def test_mixed_precision_step_close_to_fp32(cuda):
         # dense per-point path (backbone forward -> conv1d_block -> recon_head -> Chamfer/recon
         # terms): smooth in the activations, so bf16 must track fp32 closely
         dense = cos(lambda n: ("conv1d_block" in n or "recon_head" in n) and n.endswith("weight"))
-        assert dense > 0.97, dense
+        assert dense > dense_bar, dense
         # everything else is routed through max-over-points and a batch-stat BN over the 8 objects
         # of this batch (PoseR.py:29-35): discontinuous in the activations, bf16 rounding re-routes
         # winners (measured per-parameter cosines 0.5-0.98, tools/debug_mixed.py) — sanity bound only
@@ -318,34 +322,38 @@ def test_mixed_precision_step_close_to_fp32(cuda):
 
 
 def test_cuda_graph_step_matches_eager(cuda):
-    """engine.TrainStep: the step replayed from one CUDA graph follows the eagerly launched
-    step (same CPU-generator pooling permutations, dropout/augmentation off)."""
+    """engine.TrainStep: six optimiser steps replayed from one CUDA graph follow the eagerly launched
+    loop (same CPU-generator pooling permutations, dropout/augmentation off).  The graph warm-up is
+    side-effect free, so step 0 sees identical weights.  Float atomics in the gather backward make even
+    two EAGER runs differ after the first update; the bar is 3x that measured eager-vs-eager noise."""
     from hspose_b200.engine import TrainStep
     from hspose_b200.HSPose import HSPose
     F = _flags()
     saved = {n: getattr(F, n) for n in ("aug_pc_pro", "aug_rt_pro", "aug_bb_pro", "aug_bc_pro")}
     for n in saved:
         setattr(F, n, 0.0)
+
+    def run(graph):
+        F.train, F.gcn_n_num = 1, 20
+        net = fill_params(HSPose("PoseNet_only", chamfer_w=1.0)).to(cuda).train()
+        for m in net.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        tr = TrainStep(net, lr=1e-5, amp=True, graph=graph)
+        torch.manual_seed(77)
+        out = []
+        for i in range(6):   # graph mode: the first call warms up (side-effect free) and captures
+            out.append(tr(synth_batch(4, 1028, seed=10 + (i % 2), train=True)).item())
+        if graph:
+            assert tr.launches_per_step and tr.launches_per_step > 50
+        return np.array(out)
     try:
-        losses = {}
-        for mode in ("eager", "graph"):
-            F.train, F.gcn_n_num = 1, 20
-            net = fill_params(HSPose("PoseNet_only", chamfer_w=1.0)).to(cuda).train()
-            for m in net.modules():
-                if isinstance(m, torch.nn.Dropout):
-                    m.p = 0.0
-            tr = TrainStep(net, lr=1e-3, amp=True, graph=(mode == "graph"))
-            torch.manual_seed(77)
-            out = []
-            for i in range(6):   # graph mode: the first call runs 3 eager warm-up steps + capture
-                batch = synth_batch(4, 1028, seed=10 + (i % 2), train=True)
-                out.append(tr(batch).item())
-            losses[mode] = out
-            if mode == "graph":
-                assert tr.launches_per_step and tr.launches_per_step > 50
-        # graph mode consumed 3 extra warm-up updates before its first replay: compare the
-        # trend only (both must decrease and stay finite), then exact-ish agreement of a fresh pair
-        assert all(np.isfinite(losses["eager"])) and all(np.isfinite(losses["graph"]))
+        e1, e2, g = run(False), run(False), run(True)
+        assert np.all(np.isfinite(e1)) and np.all(np.isfinite(g))
+        assert abs(e1[0] - g[0]) <= 1e-3 * abs(e1[0]), (e1, g)          # identical weights at step 0
+        noise = np.abs(e1 - e2) / np.abs(e1)
+        diff = np.abs(e1 - g) / np.abs(e1)
+        assert np.all(diff <= 3.0 * noise + 1e-3), (e1, e2, g)
     finally:
         for n, v in saved.items():
             setattr(F, n, v)
@@ -378,3 +386,83 @@ def test_cuda_graph_replay_equals_eager_single_step(cuda):
     finally:
         for n, v in saved.items():
             setattr(F, n, v)
+
+
+def test_fused_loss_kernel_matches_loss_modules(cuda):
+    """K8 (csrc/losses.cu: one templated per-object function evaluated with forward-mode dual numbers +
+    two point passes) against the tensor-algebra loss modules of losses.py — which tests/test_losses_cpu.py
+    pins to the reference's own modules — on synthetic predictions covering every symmetry branch:
+    all 19 terms and the gradients w.r.t. every prediction."""
+    import hspose_b200.ops as ops
+    from hspose_b200.losses import fs_net_loss, geo_transform_loss, prop_rot_loss, recon_6face_loss
+    from hspose_b200.geom import get_gt_v
+    from hspose_b200.synth import synth_predictions
+    F = _flags()
+    B, N = 12, 257
+    pred, gt = synth_predictions(B, N, seed=11)
+    g = torch.Generator().manual_seed(5)
+    face_raw = torch.cat([(pred["face_normal"] * (0.5 + torch.rand(B, N, 6, 1, generator=g))).reshape(B, N, 18),
+                          pred["face_dis"], torch.logit(pred["face_f"])], dim=2)
+    dev = {k: v.to(cuda) for k, v in gt.items()}
+
+    def leaves():
+        out = {k: pred[k].to(cuda).clone().requires_grad_() for k in
+               ("recon", "p_green_R", "p_red_R", "f_green_R", "f_red_R", "Pred_T", "Pred_s")}
+        out["face"] = face_raw.to(cuda).clone().requires_grad_()
+        return out
+    # reference path: the modules, from the same raw face tensor (normalise / sigmoid as PoseNet9D.py:28-33)
+    a = leaves()
+    fn = a["face"][:, :, :18].view(B, N, 6, 3)
+    fn = fn / torch.norm(fn, dim=-1, keepdim=True)
+    fd, fc = a["face"][:, :, 18:24], torch.sigmoid(a["face"][:, :, 24:])
+    gg, gr = get_gt_v(dev["gt_R"])
+    names = (['Rot1', 'Rot2', 'Rot1_cos', 'Rot2_cos', 'Rot_regular', 'Tran', 'Size', 'R_con'],
+             ['Per_point', 'Point_voting'], ['Geo_point'], ['Prop_pm', 'Prop_sym'])
+    ref = {}
+    ref.update(fs_net_loss()(names[0], {'Rot1': a["p_green_R"], 'Rot1_f': a["f_green_R"], 'Rot2': a["p_red_R"],
+                                        'Rot2_f': a["f_red_R"], 'Recon': a["recon"], 'Tran': a["Pred_T"],
+                                        'Size': a["Pred_s"]},
+                             {'Rot1': gg, 'Rot2': gr, 'Recon': dev["PC"], 'Tran': dev["gt_t"], 'Size': dev["gt_s"]},
+                             dev["sym"]))
+    ref.update(recon_6face_loss().to(cuda)(names[1], {'F_n': fn, 'F_d': fd, 'F_c': fc, 'Rot1': a["p_green_R"],
+                                                      'Rot1_f': a["f_green_R"].detach(), 'Rot2': a["p_red_R"],
+                                                      'Rot2_f': a["f_red_R"].detach(), 'Tran': a["Pred_T"],
+                                                      'Size': a["Pred_s"]},
+                                           {'R': dev["gt_R"], 'T': dev["gt_t"], 'Size': dev["gt_s"],
+                                            'Mean_shape': dev["mean_shape"], 'Points': dev["PC"]}, dev["sym"],
+                                           dev["obj_id"]))
+    ref.update(geo_transform_loss()(names[2], {'Rot1': a["p_green_R"], 'Rot2': a["p_red_R"], 'Tran': a["Pred_T"]},
+                                    {'Points': dev["PC"], 'R': dev["gt_R"], 'T': dev["gt_t"]}, dev["sym"]))
+    ref.update(prop_rot_loss().to(cuda)(names[3], {'Recon': a["recon"], 'Rot1': a["p_green_R"], 'Rot2': a["p_red_R"],
+                                                   'Tran': a["Pred_T"], 'Rot1_f': a["f_green_R"].detach(),
+                                                   'Rot2_f': a["f_red_R"].detach()},
+                                        {'Points': dev["PC"], 'R': dev["gt_R"], 'T': dev["gt_t"]}, dev["sym"]))
+    b = leaves()
+    w = [getattr(F, n) for n in ops.LOSS_WEIGHT_FLAGS]
+    got = ops.fused_losses(w, b["face"], b["recon"], b["p_green_R"], b["p_red_R"], b["f_green_R"], b["f_red_R"],
+                           b["Pred_T"], b["Pred_s"], dev["PC"], dev["gt_R"], dev["gt_t"], dev["gt_s"],
+                           dev["mean_shape"], dev["sym"], dev["obj_id"])
+    assert set(got) == set(ref), (sorted(got), sorted(ref))
+    for k in got:
+        r = ref[k].item()
+        assert abs(got[k].item() - r) <= 2e-5 * max(1.0, abs(r)), (k, got[k].item(), r)
+    # gradients, term group by term group (so a wrong term cannot hide behind a large one)
+    groups = {"fs": names[0], "recon": ["recon_"], "geo": ["geo_"], "prop": ["Prop_"]}
+    for gname in ("fs", "recon", "geo", "prop"):
+        keys = [k for k in got if (k.startswith(tuple(groups[gname])) if gname != "fs" else
+                                   k in ("Rot1", "Rot1_cos", "Rot2", "Rot2_cos", "Rot_r_a", "Tran", "Size", "R_con"))]
+        for d in (a, b):
+            for v in d.values():
+                v.grad = None
+        sum(ref[k] for k in keys).backward(retain_graph=True)
+        sum(got[k] for k in keys).backward(retain_graph=True)
+        for name in a:
+            ga, gb = a[name].grad, b[name].grad
+            if ga is None or float(ga.abs().max()) == 0.0:
+                assert gb is None or float(gb.abs().max()) == 0.0, (gname, name)
+                continue
+            assert gb is not None, (gname, name)
+            # plane-fit gradients: fp32 noise floor 1e-4..3e-4 of the tensor max (tests/test_losses_cpu.py)
+            rel = 1e-3 if gname == "recon" and name in ("face", "Pred_T") else 5e-5
+            err = (ga - gb).abs().max().item()
+            assert err <= rel * ga.abs().max().item() + 1e-9, (gname, name, err, ga.abs().max().item())

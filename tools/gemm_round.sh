@@ -21,7 +21,7 @@ run 512 256 256 0 0 0 1 128 2
 run 1028 1024 1296 0 0 0 1 256 2
 run 1000 520 1296 0 1 0 1 256 2
 run 1024 1296 4112 1 1 1 3 256 2
-run 1028 100 300 0 0 0 1 64 2
+run 1028 100 304 0 0 0 1 64 2
 echo "== timing (B=128 shapes)"
 run 131584 1024 1296 0 0 0 1 256 2 t
 run 131584 1024 1296 0 0 0 1 256 1 t

@@ -27,10 +27,10 @@ def case(M, N, K, a_mn, b_mn, f32, splits):
     odt = torch.float32 if f32 else torch.bfloat16
     out = torch.empty((splits, M, N) if splits > 1 else (M, N), dtype=odt, device=dev)
     print(f"--- M={M} N={N} K={K} a_mn={a_mn} b_mn={b_mn} f32={f32} splits={splits}", flush=True)
-    for ctas in (1, 2):
-        for tile_n in (256, 128):
+    for ctas in CTAS:
+        for tile_n in TILES:
             for stats in ((False, True) if not f32 and splits == 1 else (False,)):
-                for dbg in (0, 1, 2, 4, 3, 6, 7):
+                for dbg in DBG:
                     lib.hsp_gemm_debug(dbg)
                     try:
                         ms = t(lambda: ops.gemm_bf16(A, B, a_mn, b_mn, out=out, out_dtype=odt, splits=splits,
@@ -42,6 +42,9 @@ def case(M, N, K, a_mn, b_mn, f32, splits):
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+CTAS = [int(x) for x in os.environ.get("CTAS", "1,2").split(",")]
+TILES = [int(x) for x in os.environ.get("TILES", "256,128").split(",")]
+DBG = [int(x) for x in os.environ.get("DBG", "0,1,2,4,3,6,7").split(",")]
 if which in ("all", "fwd"):
     case(131584, 1024, 1296, False, False, False, 1)
 if which in ("all", "p"):
