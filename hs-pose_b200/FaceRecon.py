@@ -48,6 +48,12 @@ def conv1x1(conv: nn.Conv1d, x_bnc, pad_in=0, pad_out=0):
     """nn.Conv1d(kernel_size=1) applied in (bs, N, C) layout.  pad_in / pad_out append
     zero input columns / output rows to the weight so GEMM dims stay 16-byte aligned."""
     w, b = conv.weight[:, :, 0], conv.bias
+    if mixed_precision() and x_bnc.is_cuda:
+        # K6 tensor-core GEMM (forward, dgrad, wgrad); the kernel pads / clips ragged widths itself
+        if pad_in:
+            w = F.pad(w, (0, pad_in))
+        y = ops.linear_tc(x_bnc, w, b)
+        return F.pad(y, (0, pad_out)) if pad_out else y
     if pad_in or pad_out:
         w = F.pad(w, (0, pad_in, 0, pad_out))
         if b is not None and pad_out:
@@ -114,10 +120,7 @@ def seq_points(seq: nn.Sequential, x_bnc):
             continue
         if isinstance(m, nn.Conv1d):
             pad_in = x_bnc.shape[-1] - m.in_channels
-            pad_out = (-m.out_channels) % 8 if mixed_precision() else 0
-            x_bnc = conv1x1(m, x_bnc, pad_in, pad_out)
-            if pad_out:
-                x_bnc = x_bnc[..., :m.out_channels]
+            x_bnc = conv1x1(m, x_bnc, pad_in)
         elif isinstance(m, nn.BatchNorm1d):
             fuse = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
             x_bnc = bn_points(m, x_bnc, relu=fuse)
@@ -238,10 +241,9 @@ class FaceRecon(nn.Module):
         conv0 = self.face_head[0]
         w = conv0.weight[:, :, 0]
         cg = f_global.shape[1]
-        per_obj = F.linear(f_global, w[:, :cg], conv0.bias)                     # (bs, 512)
+        per_obj = ops.linear_tc(f_global, w[:, :cg], conv0.bias)                 # (bs, 512)
         tail = torch.cat([conv1d_out, vertices.to(conv1d_out.dtype)], dim=2)     # (bs, N, 259)
         pad = (-tail.shape[2]) % 8
         tail = F.pad(tail, (0, pad))
-        x = torch.baddbmm(per_obj.unsqueeze(1), tail,
-                          F.pad(w[:, cg:], (0, pad)).t().unsqueeze(0).expand(bs, -1, -1))
+        x = ops.linear_tc(tail, F.pad(w[:, cg:], (0, pad))) + per_obj.unsqueeze(1)
         return seq_points(list(self.face_head)[1:], x)

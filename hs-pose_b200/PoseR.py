@@ -10,7 +10,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .FaceRecon import conv_bn_relu_points
+from .FaceRecon import conv_bn_relu_points, mixed_precision
 from .flags import FLAGS
 
 
@@ -37,9 +37,10 @@ class _PointHead(nn.Module):
             x = ops.colmax(x)                                   # (bs, 256): max over points
         else:
             x = torch.max(x, 1)[0]
-        x = F.relu(self.bn3(F.linear(x, self.conv3.weight[:, :, 0], self.conv3.bias)))
+        lin = ops.linear_tc if (mixed_precision() and x.is_cuda) else F.linear   # K6 on the mixed-precision path
+        x = F.relu(self.bn3(lin(x, self.conv3.weight[:, :, 0], self.conv3.bias)))
         x = self.drop1(x)
-        x = F.linear(x, self.conv4.weight[:, :, 0], self.conv4.bias)
+        x = lin(x, self.conv4.weight[:, :, 0], self.conv4.bias)
         return x.contiguous()
 
     def forward(self, x):

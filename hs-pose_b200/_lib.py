@@ -47,6 +47,10 @@ SIGNATURES = {
     "hsp_losses_num_sums": (c_int, []),
     "hsp_losses_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, P, P, P]),
     "hsp_losses_bwd": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, P, P, P, P, P]),
+    "hsp_optim_workspace_bytes": (c_size_t, []),
+    "hsp_optim_step": (c_int, [c_int, P, P, P, P, P, ctypes.c_long, P, P, c_int, P, P, ctypes.c_float, ctypes.c_float,
+                               ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_int, c_int, P, P,
+                               c_size_t, P]),
     "hsp_residual_sum_fwd": (c_int, [P, P, c_int, P, P, c_int, P, P, c_int, c_int, c_int, P, P]),
     "hsp_residual_sum_bwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P]),
     "hsp_colmax_fwd": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P]),

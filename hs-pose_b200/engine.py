@@ -14,7 +14,7 @@ import copy
 
 import torch
 
-from . import gcn3d, ops, parallel
+from . import gcn3d, ops, optim, parallel
 
 _RING = 4   # pinned staging slots per Pool_layer permutation (bounds how far the CPU may run ahead)
 
@@ -49,9 +49,13 @@ class TrainStep:
                  tf32=False):
         self.model, self.clip, self.amp, self.use_graph = model, clip, amp, graph
         self.flat = parallel.FlatGradients(model.posenet.parameters())
-        # default optimiser: Adam over ONE flat parameter (see FlatGradients.flatten_params)
-        self.opt = optimizer or torch.optim.Adam([self.flat.flatten_params()], lr=lr, fused=True,
-                                                 capturable=graph)
+        # optimiser: "adam" (BASELINE.json configs[2]) or "ranger" (the reference's, tools/solver_utils.py:49-50)
+        # = the K9 kernels over ONE flat parameter buffer with the clip folded in; a torch.optim.Optimizer
+        # instance is also accepted (then `clip` runs as a separate pass)
+        if optimizer is None or isinstance(optimizer, str):
+            self.opt = optim.FlatOptimizer(self.flat, kind=optimizer or "adam", lr=lr, clip=clip)
+        else:
+            self.opt = optimizer
         self.graph = None
         self.static_batch = None
         self.static_loss = None
@@ -102,9 +106,12 @@ class TrainStep:
         finally:
             gcn3d.set_pool_rows_provider(prev)
         self.flat.all_reduce_mean()
-        if self.clip:
-            self.flat.clip_(self.clip)
-        self.opt.step()
+        if isinstance(self.opt, optim.FlatOptimizer):
+            self.opt.step()                       # clip + update, three launches
+        else:
+            if self.clip:
+                self.flat.clip_(self.clip)
+            self.opt.step()
         return total.detach()
 
     def _capture(self, batch):
@@ -135,7 +142,8 @@ class TrainStep:
         dev = next(self.model.parameters()).device
         return {"params": [p.detach().clone() for p in self.model.parameters()],
                 "buffers": [b.detach().clone() for b in self.model.buffers()],
-                "opt": copy.deepcopy(self.opt.state_dict()),
+                "opt": self.opt.state_dict() if isinstance(self.opt, optim.FlatOptimizer)
+                else copy.deepcopy(self.opt.state_dict()),
                 "cpu_rng": torch.get_rng_state(), "cuda_rng": torch.cuda.get_rng_state(dev)}
 
     def _restore(self, snap):
@@ -145,6 +153,12 @@ class TrainStep:
                 p.copy_(q)
             for b, q in zip(self.model.buffers(), snap["buffers"]):
                 b.copy_(q)
+            if isinstance(self.opt, optim.FlatOptimizer):
+                self.opt.load_state_dict(snap["opt"])      # copies in place
+                self.flat.zero()
+                torch.set_rng_state(snap["cpu_rng"])
+                torch.cuda.set_rng_state(snap["cuda_rng"], dev)
+                return
             # optimiser state IN PLACE (the captured graph holds these tensors' addresses): a state that
             # did not exist before the warm-up (first step) goes back to its initial value, zero
             old = snap["opt"]["state"]

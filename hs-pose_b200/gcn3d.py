@@ -151,9 +151,13 @@ def _orl_fuse(feature, vertices, neighbor_num, conv2_weight, f_STE=None, ste_xyz
     C = feature.shape[2]
     G = ops.orl_global(feature, _geo_index32_exact(vertices, neighbor_num))  # (B,C)
     W2 = conv2_weight[:, :, 0]
-    lin = F.linear(feature, W2[:, :C])
-    with torch.autocast("cuda", enabled=False):
-        gproj = F.linear(G.float(), W2[:, C:].float())                       # (B,C), tiny: keep fp32
+    if torch.is_autocast_enabled("cuda") and feature.is_cuda and C % 8 == 0:
+        lin = ops.linear_tc(feature, W2[:, :C])                              # K6 (bf16 operands, fp32 accumulate)
+        gproj = ops.linear_tc(G, W2[:, C:]).float()                          # (B,C)
+    else:
+        lin = F.linear(feature, W2[:, :C])
+        with torch.autocast("cuda", enabled=False):
+            gproj = F.linear(G.float(), W2[:, C:].float())                   # (B,C)
     if C % 4 == 0 and feature.dtype == torch.float32:
         if ste_xyz_weight is not None:   # surface layer: STE = 3 -> C linear on xyz, evaluated in the same pass
             return ops.residual_sum(feature, lin, gproj, None, vertices.float(), ste_xyz_weight.float())
@@ -227,7 +231,10 @@ class HS_layer(nn.Module):
         self.directions.data.uniform_(-stdv, stdv)
 
     def forward(self, vertices, feature_map, neighbor_num):
-        f_STE = F.linear(feature_map, self.STE_layer.weight[:, :, 0])
+        if torch.is_autocast_enabled("cuda") and feature_map.is_cuda and self.in_channel % 8 == 0:
+            f_STE = ops.linear_tc(feature_map, self.STE_layer.weight[:, :, 0])    # K6
+        else:
+            f_STE = F.linear(feature_map, self.STE_layer.weight[:, :, 0])
         neighbor_index = _feature_index32(feature_map, neighbor_num)          # RF-F (K2)
         feature = self.graph_conv(None, neighbor_index, feature_map, vertices, neighbor_num)
         return _orl_fuse(feature, vertices, neighbor_num, self.conv2.weight, f_STE)

@@ -17,7 +17,7 @@ F32, BF16 = 0, 1   # HSP_DTYPE_*
 _launches = 0  # number of CUDA kernels launched through the C ABI (bench.py reads this)
 
 # kernels launched per entry point (memsets not counted)
-_KERNELS_PER_CALL = {"hsp_losses_fwd": 2, "hsp_losses_bwd": 2, "hsp_bn_apply_fwd": 2, "hsp_knn_feat": 2, "hsp_surface_conv_bwd": 2, "hsp_graph_conv_bwd": 2,
+_KERNELS_PER_CALL = {"hsp_optim_step": 3, "hsp_losses_fwd": 2, "hsp_losses_bwd": 2, "hsp_bn_apply_fwd": 2, "hsp_knn_feat": 2, "hsp_surface_conv_bwd": 2, "hsp_graph_conv_bwd": 2,
                      "hsp_orl_global_fwd": 2, "hsp_chamfer_fwd": 2, "hsp_chamfer_bwd": 2,
                      "hsp_bn_relu_fwd": 3, "hsp_bn_relu_bwd": 3}
 

@@ -296,6 +296,25 @@ int hsp_losses_bwd(const float* face, const float* recon, const float* PC, const
                    int B, int N, float* gface, float* grecon, float* gpred, float* gmom_ws,
                    void* stream);
 
+/* ------------------------------------------------------------------ K9 ---
+ * clip_grad_norm_ + optimiser step over flat fp32 buffers of n elements, three launches.
+ *   kind 1 = Ranger (RAdam + Lookahead + gradient centralisation): tools/torch_utils/solver/ranger2020.py:135-246
+ *            (the reference's optimiser, tools/solver_utils.py:49-50), gc_loc = True, gc_conv_only = False;
+ *   kind 0 = Adam (torch.optim.Adam semantics; BASELINE.json configs[2] names Adam).
+ * Clipping as engine/train.py:107 (`clip_grad_norm_(.., 5)`): coef = min(1, clip_max_norm / (||g|| + 1e-6)),
+ * folded into the update (grad is not modified); clip_max_norm <= 0 disables it.
+ * Segments describe the flat buffer: seg_len > 0 = one row of a >= 2-D parameter (its mean is subtracted
+ * from the gradient: gradient centralisation), seg_len < 0 = |seg_len| elements without centralisation.
+ * `step` (device int32) is incremented on the device and `lr` is read from device memory, so the call can
+ * live inside a CUDA graph.  slow: Lookahead weights (Ranger; initialised by the caller to the parameters).
+ * grad_norm_out (device, optional) receives ||g|| before clipping.  Deterministic.                     */
+size_t hsp_optim_workspace_bytes(void);
+int hsp_optim_step(int kind, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                   float* slow, long n, const int* seg_off, const int* seg_len, int nseg, int* step,
+                   const float* lr, float beta1, float beta2, float eps, float weight_decay,
+                   float clip_max_norm, float alpha, int k, int nsma_threshold, float* grad_norm_out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

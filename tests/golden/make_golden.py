@@ -198,6 +198,32 @@ def golden_e2e_eval(FLAGS, gcn3d):
     save("e2e_eval", **arrays)
 
 
+def golden_e2e_eval_b16(FLAGS, gcn3d):
+    """BASELINE.json configs[1] as written: batch = 16, N = 1028, fp32 forward only, KNN k = 16 (and the
+    shipped k = 20): the six pose / size outputs and the RF-F neighbour tables of the reference run."""
+    sys.path.insert(0, ROOT)
+    from hspose_b200.synth import fill_params, synth_batch
+    from network.fs_net_repo.PoseNet9D import PoseNet9D
+    FLAGS.train = 0
+    arrays = {}
+    for k in (16, 20):
+        FLAGS.gcn_n_num = k
+        net = fill_params(PoseNet9D()).eval()
+        batch = synth_batch(16, 1028, seed=1, train=False)
+        log, undo = _rf_recorder(gcn3d)
+        torch.manual_seed(1234)
+        with torch.no_grad():
+            out = net(batch["PC"], batch["obj_id"])
+        undo()
+        for n, t in zip(["p_green_R", "p_red_R", "f_green_R", "f_red_R", "Pred_T", "Pred_s"], out[4:]):
+            arrays[f"k{k}_{n}"] = t
+        for i, r in enumerate(log):
+            arrays[f"k{k}_rf{i}"] = small_idx(r)
+    FLAGS.gcn_n_num = 20
+    FLAGS.train = 1
+    save("e2e_eval_b16", **arrays)
+
+
 def golden_e2e_train(FLAGS, gcn3d):
     """HSPose('PoseNet_only') train-mode step as engine/train.py:76-107 runs it: forward with
     do_loss=True, sum of all loss terms, backward.  Dropout p=0 and augmentation
@@ -330,20 +356,47 @@ def golden_losses(FLAGS):
     save("losses", **arrays)
 
 
+def golden_optim():
+    """The reference's Ranger (tools/torch_utils/solver/ranger2020.py) preceded by
+    clip_grad_norm_(.., 5) as engine/train.py:105-110 runs it, 8 steps (lookahead fires at 6) on a
+    small parameter set with seeded gradients; parameters saved after steps 1, 5, 6 and 8."""
+    from tools.torch_utils.solver.ranger2020 import Ranger
+    shapes = [(8, 16), (16,), (4, 8, 1), (3, 24), (5,), (32, 40)]
+    g = torch.Generator().manual_seed(21)
+    params = [torch.nn.Parameter(torch.randn(s, generator=g) * 0.3) for s in shapes]
+    arrays = {f"p0_{i}": p.detach().clone() for i, p in enumerate(params)}
+    opt = Ranger(params, lr=1e-2)
+    for step in range(1, 9):
+        scale = 30.0 if step in (2, 7) else 0.5          # steps 2 and 7 exceed the clip norm of 5
+        for i, p in enumerate(params):
+            p.grad = torch.randn(p.shape, generator=g) * scale
+            arrays[f"g{step}_{i}"] = p.grad.clone()
+        arrays[f"norm{step}"] = torch.nn.utils.clip_grad_norm_(params, 5.0)
+        opt.step()
+        if step in (1, 5, 6, 8):
+            for i, p in enumerate(params):
+                arrays[f"p{step}_{i}"] = p.detach().clone()
+    save("optim", **arrays)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     _args = sys.argv[1:]
     FLAGS, gcn3d = import_reference()
-    which = _args or ["knn", "ops", "e2e_eval", "e2e_train", "aug", "losses"]
+    which = _args or ["knn", "ops", "e2e_eval", "e2e_train", "aug", "losses", "optim", "e2e_eval_b16"]
     if "knn" in which:
         golden_knn(gcn3d)
     if "ops" in which:
         golden_ops(gcn3d)
     if "e2e_eval" in which:
         golden_e2e_eval(FLAGS, gcn3d)
+    if "e2e_eval_b16" in which:
+        golden_e2e_eval_b16(FLAGS, gcn3d)
     if "e2e_train" in which:
         golden_e2e_train(FLAGS, gcn3d)
     if "aug" in which:
         golden_augment(FLAGS)
     if "losses" in which:
         golden_losses(FLAGS)
+    if "optim" in which:
+        golden_optim()

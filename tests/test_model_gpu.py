@@ -37,13 +37,13 @@ def _posenet(cuda, train, k=20):
     return m
 
 
-def _run_eval(cuda, golden, k, forced):
+def _run_eval(cuda, golden, k, forced, bs=2):
     from hspose_b200 import gcn3d
-    g = golden("e2e_eval")
+    g = golden("e2e_eval" if bs == 2 else f"e2e_eval_b{bs}")
     F = _flags()
     net = _posenet(cuda, 0, k).eval()
     try:
-        batch = synth_batch(2, 1028, seed=1, train=False)
+        batch = synth_batch(bs, 1028, seed=1, train=False)
         rec = []
         torch.manual_seed(1234)
         with torch.no_grad(), gcn3d.record_rf_indices(rec):
@@ -58,9 +58,10 @@ def _run_eval(cuda, golden, k, forced):
     return g, dict(zip(NAMES, [t.cpu().numpy() for t in out[4:]])), rec
 
 
+@pytest.mark.parametrize("bs", [2, 16])      # 16 = BASELINE.json configs[1] as written (batch 16, k = 16)
 @pytest.mark.parametrize("k", [20, 16])
-def test_posenet_eval_teacher_forced_1e5(cuda, golden, k):
-    g, out, _ = _run_eval(cuda, golden, k, forced=True)
+def test_posenet_eval_teacher_forced_1e5(cuda, golden, k, bs):
+    g, out, _ = _run_eval(cuda, golden, k, forced=True, bs=bs)
     for n in NAMES:
         np.testing.assert_allclose(out[n], g[f"k{k}_{n}"], atol=1e-5, err_msg=n)
 
