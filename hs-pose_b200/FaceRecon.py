@@ -241,9 +241,19 @@ class FaceRecon(nn.Module):
         conv0 = self.face_head[0]
         w = conv0.weight[:, :, 0]
         cg = f_global.shape[1]
-        per_obj = ops.linear_tc(f_global, w[:, :cg], conv0.bias)                 # (bs, 512)
-        tail = torch.cat([conv1d_out, vertices.to(conv1d_out.dtype)], dim=2)     # (bs, N, 259)
-        pad = (-tail.shape[2]) % 8
-        tail = F.pad(tail, (0, pad))
+        per_obj = ops.linear_tc(f_global, w[:, :cg], conv0.bias).float()         # (bs, 512)
+        pad = (-(conv1d_out.shape[2] + 3)) % 8
+        tail = torch.cat([conv1d_out, vertices.to(conv1d_out.dtype),
+                          conv1d_out.new_zeros(bs, n, pad)], dim=2)              # (bs, N, 264): one pass, 16-B rows
+        bn0 = self.face_head[1]
+        if bn0.training and n > 1:
+            # face_head[0..2] = conv -> BN -> ReLU as one K6/K6b node; the f_global block enters the GEMM
+            # epilogue as a per-object bias (no (bs, N, 512) broadcast add)
+            if bn0.num_batches_tracked is not None:
+                bn0.num_batches_tracked += 1
+            z = ops.linear_bn_relu(tail.view(bs * n, -1), F.pad(w[:, cg:], (0, pad)), None, bn0.weight, bn0.bias,
+                                   bn0.running_mean, bn0.running_var, bn0.eps, bn0.momentum, True,
+                                   bias_rows=per_obj.contiguous(), rows_per_group=n)
+            return seq_points(list(self.face_head)[3:], z.view(bs, n, -1))
         x = ops.linear_tc(tail, F.pad(w[:, cg:], (0, pad))) + per_obj.unsqueeze(1)
         return seq_points(list(self.face_head)[1:], x)

@@ -141,6 +141,17 @@ class HSPose(nn.Module):
         """Reference HSPose.py:185-256: four Bernoulli-gated deformations; the device RNG is
         consumed in the same order (prob_bb, prob_rt, prob_bc, ey_up, ey_down, prob_pc, defor)."""
         bs = PC.shape[0]
+        if PC.is_cuda and not check_points:
+            # K10: one launch; the uniform draws keep the reference's order and shapes
+            dev = PC.device
+            g_bb, g_rt, g_bc = (torch.rand((bs, 1), device=dev) for _ in range(3))
+            ey_up, ey_down = torch.rand((bs, 1), device=dev), torch.rand((bs, 1), device=dev)
+            g_pc = torch.rand((bs, 1), device=dev)
+            defor = torch.rand(PC.shape, device=dev)
+            return ops.augment(PC, gt_R, gt_t, gt_s, mean_shape, sym, aug_bb, aug_rt_t, aug_rt_r, model_point,
+                               nocs_scale, obj_ids, torch.cat([g_bb, g_rt, g_bc, g_pc], dim=1),
+                               torch.cat([ey_up, ey_down], dim=1), defor,
+                               (FLAGS.aug_bb_pro, FLAGS.aug_rt_pro, FLAGS.aug_bc_pro, FLAGS.aug_pc_pro), FLAGS.aug_pc_r)
         flag = torch.rand((bs, 1), device=PC.device) < FLAGS.aug_bb_pro
         PC_new, s_new, mp_new = augment.deform_bb(PC, model_point, gt_R, gt_t, gt_s + mean_shape, sym, aug_bb)
         PC = torch.where(flag.unsqueeze(-1), PC_new, PC)

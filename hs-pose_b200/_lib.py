@@ -41,7 +41,7 @@ SIGNATURES = {
                                  c_int, P, P, P, P, P, P, c_int, P]),
     "hsp_gemm_bf16_splits": (c_int, [c_int] * 4),
     "hsp_gemm_debug": (c_int, [c_int]),
-    "hsp_gemm_bf16": (c_int, [P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int,
+    "hsp_gemm_bf16": (c_int, [P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, c_int, c_int,
                               c_int, P, c_int, c_int, P]),
     "hsp_losses_num_terms": (c_int, []),
     "hsp_losses_num_sums": (c_int, []),
@@ -51,6 +51,7 @@ SIGNATURES = {
     "hsp_optim_step": (c_int, [c_int, P, P, P, P, P, ctypes.c_long, P, P, c_int, P, P, ctypes.c_float, ctypes.c_float,
                                ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_int, c_int, P, P,
                                c_size_t, P]),
+    "hsp_augment": (c_int, [P] * 15 + [ctypes.c_float] * 5 + [c_int] * 3 + [P] * 5),
     "hsp_residual_sum_fwd": (c_int, [P, P, c_int, P, P, c_int, P, P, c_int, c_int, c_int, P, P]),
     "hsp_residual_sum_bwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P]),
     "hsp_colmax_fwd": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P]),

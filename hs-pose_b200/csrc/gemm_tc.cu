@@ -206,6 +206,8 @@ struct Params {
   int splits;           // split-K factor (partials in planes of the 3-D output map)
   int kb_per_split;     // 64-element k-blocks per split
   const float* bias;    // (N) or NULL
+  const float* bias_rows;   // (ceil(M / rows_per_group), N) or NULL: a second bias, shared by groups of consecutive rows
+  int rows_per_group;
   float* stats;         // (ceil(M/128), 2, N) per-row-block column sums / sums of squares, or NULL
   int debug;            // diagnostics (hsp_gemm_debug): 1 = no staging writes / stores, 2 = no MMAs, 4 = no TMA loads
 };
@@ -410,6 +412,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         unsigned char* srow = so + row * 128;
         const float4* bs4 = reinterpret_cast<const float4*>(bs_tile + ch * OUT_COLS);
         const bool add_bias = p.bias != nullptr && (full_rows || row_ok);
+        // per-row-group bias (e.g. a per-object term broadcast over the object's points): this thread's row
+        const float* brow = nullptr;
+        if (p.bias_rows != nullptr && (full_rows || row_ok))
+          brow = p.bias_rows + (size_t)((m0 + row) / p.rows_per_group) * p.N + n0 + ch * OUT_COLS;
+        const bool brow_vec = n0 + (ch + 1) * OUT_COLS <= p.N;     // whole chunk inside the matrix: vector loads
         if (OUT_F32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {           // 8 x 16 bytes = 32 floats
@@ -418,6 +425,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (add_bias) {
               const float4 b4 = bs4[j];
               o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            }
+            if (brow) {
+              float r4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                r4[e] = (brow_vec || n0 + ch * OUT_COLS + 4 * j + e < p.N) ? __ldg(brow + 4 * j + e) : 0.f;
+              o.x += r4[0]; o.y += r4[1]; o.z += r4[2]; o.w += r4[3];
             }
             *reinterpret_cast<float4*>(srow + ((j ^ (row & 7)) << 4)) = o;
           }
@@ -434,6 +448,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               f[1] = __fadd2_rn(f[1], make_float2(b0.z, b0.w));
               f[2] = __fadd2_rn(f[2], make_float2(b1.x, b1.y));
               f[3] = __fadd2_rn(f[3], make_float2(b1.z, b1.w));
+            }
+            if (brow) {
+              if (brow_vec) {
+                const float4 r0 = __ldg(reinterpret_cast<const float4*>(brow) + 2 * j);
+                const float4 r1 = __ldg(reinterpret_cast<const float4*>(brow) + 2 * j + 1);
+                f[0] = __fadd2_rn(f[0], make_float2(r0.x, r0.y));
+                f[1] = __fadd2_rn(f[1], make_float2(r0.z, r0.w));
+                f[2] = __fadd2_rn(f[2], make_float2(r1.x, r1.y));
+                f[3] = __fadd2_rn(f[3], make_float2(r1.z, r1.w));
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int c0 = n0 + ch * OUT_COLS + 8 * j + 2 * e;
+                  f[e].x += c0 < p.N ? __ldg(brow + 8 * j + 2 * e) : 0.f;
+                  f[e].y += c0 + 1 < p.N ? __ldg(brow + 8 * j + 2 * e + 1) : 0.f;
+                }
+              }
             }
             uint4 o;
             o.x = pack_bf16(f[0].x, f[0].y);
@@ -469,7 +500,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (do_stats) {
         epi_barrier();
         for (int c = etid; c < BN; c += EPI_THREADS) {
-          if (n0 + c < p.N) {
+          if (n0 + c < p.N && m0 < p.M) {      // (the last CTA pair may own a row block entirely past M)
             float s = 0.f, sq = 0.f;
 #pragma unroll
             for (int g = 0; g < 4; ++g) { s += s_part[(g * 2) * BN + c]; sq += s_part[(g * 2 + 1) * BN + c]; }
@@ -591,8 +622,8 @@ extern "C" int hsp_gemm_bf16_splits(int M, int N, int K, int out_f32) {
 }
 
 extern "C" int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M,
-                             int N, int K, const float* bias, void* out, int ldo, int out_f32, int splits,
-                             float* stats, int tile_n, int ctas, void* stream) {
+                             int N, int K, const float* bias, const float* bias_rows, int rows_per_group, void* out,
+                             int ldo, int out_f32, int splits, float* stats, int tile_n, int ctas, void* stream) {
   using namespace hsp;
   using namespace hsp::gemm;
   if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0 || splits < 1) return HSP_EINVAL;
@@ -602,7 +633,8 @@ extern "C" int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void*
     return HSP_EINVAL;
   if (lda < (a_mn_major ? M : K) || ldb < (b_mn_major ? N : K) || ldo < N) return HSP_EINVAL;
   if (stats && (out_f32 || splits != 1)) return HSP_EINVAL;
-  if (splits > 1 && (!out_f32 || bias)) return HSP_EINVAL;
+  if (splits > 1 && (!out_f32 || bias || bias_rows)) return HSP_EINVAL;
+  if (bias_rows && (rows_per_group <= 0 || (N % 4) != 0 || ((uintptr_t)bias_rows % 16) != 0)) return HSP_EINVAL;
   const int total_kb = (K + BK - 1) / BK;
   const int kb_per = (total_kb + splits - 1) / splits;
   if ((splits - 1) * kb_per >= total_kb && splits > 1) return HSP_EINVAL;
@@ -628,6 +660,7 @@ extern "C" int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void*
   p.a_mn = a_mn_major ? 1 : 0; p.b_mn = b_mn_major ? 1 : 0;
   p.splits = splits; p.kb_per_split = kb_per;
   p.bias = bias; p.stats = stats;
+  p.bias_rows = bias_rows; p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
   p.debug = g_gemm_debug;
   cudaStream_t st = (cudaStream_t)stream;
 #define HSP_GEMM_CASE(BN_, CT_)                                                          \

@@ -5,6 +5,7 @@ is one or two launches of a hand-written sm_100a kernel in libhspose_b200.so.
 No op has a PyTorch/CPU fallback — a missing library or a CPU tensor raises.
 """
 import ctypes
+import os
 
 import torch
 
@@ -60,10 +61,23 @@ def _need(t, dtype, name):
     return t if t.is_contiguous() else t.contiguous()
 
 
+_NVTX = os.environ.get("HSP_NVTX", "1") != "0"   # an NVTX range per C-ABI call (tracing hook)
+
+
 def _call(name, *args):
     global _launches
     lib = _lib.load()
     _launches += _KERNELS_PER_CALL.get(name, 1)
+    if _NVTX:
+        torch.cuda.nvtx.range_push(name)
+        try:
+            return _call_inner(lib, name, args)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    return _call_inner(lib, name, args)
+
+
+def _call_inner(lib, name, args):
     if _timing is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -635,14 +649,16 @@ class _LinearBnRelu(torch.autograd.Function):
     out of the BN-backward kernel (column sums of dY)."""
 
     @staticmethod
-    def forward(ctx, x, W, b, gamma, beta, running_mean, running_var, eps, momentum, relu):
+    def forward(ctx, x, W, b, gamma, beta, running_mean, running_var, eps, momentum, relu, bias_rows=None,
+                rows_per_group=0):
         xb = _as_gemm_operand(x)
         Wb = _as_gemm_operand(W)
-        y, part = gemm_bf16(xb, Wb, bias=b, stats=True)
+        y, part = gemm_bf16(xb, Wb, bias=b, stats=True, bias_rows=bias_rows, rows_per_group=rows_per_group)
         g32, b32 = gamma.float().contiguous(), beta.float().contiguous()
         z, stats = _bn_fwd_from_partials(y, part, g32, b32, running_mean, running_var, eps, momentum, relu)
         ctx.save_for_backward(xb, Wb, y, g32, b32, stats)
         ctx.relu, ctx.has_bias = int(relu), b is not None
+        ctx.rpg = rows_per_group if bias_rows is not None else 0
         return z
 
     @staticmethod
@@ -651,12 +667,21 @@ class _LinearBnRelu(torch.autograd.Function):
         dy, dgamma, dbeta, colsum = _bn_bwd_raw(y, dz, g32, b32, stats, ctx.relu, ctx.has_bias)
         dx = gemm_bf16(dy, Wb, b_mn=True) if ctx.needs_input_grad[0] else None
         dW = _wgrad(dy, xb)
-        return dx, dW, colsum, dgamma, dbeta, None, None, None, None, None
+        drows = None
+        if ctx.rpg:      # d bias_rows[g] = sum of dY over the group's rows
+            M, N = dy.shape
+            if M % ctx.rpg != 0:
+                raise ValueError("linear_bn_relu: bias_rows needs M % rows_per_group == 0 for the backward")
+            drows = dy.view(M // ctx.rpg, ctx.rpg, N).sum(dim=1, dtype=torch.float32)
+        return dx, dW, colsum, dgamma, dbeta, None, None, None, None, None, drows, None
 
 
-def linear_bn_relu(x, W, b, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, relu=True):
-    """Fused Linear -> BatchNorm(train) -> ReLU on a (M,K) matrix (bf16 compute)."""
-    return _LinearBnRelu.apply(x, W, b, gamma, beta, running_mean, running_var, eps, momentum, relu)
+def linear_bn_relu(x, W, b, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, relu=True,
+                   bias_rows=None, rows_per_group=0):
+    """Fused Linear -> BatchNorm(train) -> ReLU on a (M,K) matrix (bf16 compute).  bias_rows (G,N) adds a
+    second bias shared by groups of rows_per_group consecutive rows (a per-object term)."""
+    return _LinearBnRelu.apply(x, W, b, gamma, beta, running_mean, running_var, eps, momentum, relu, bias_rows,
+                               rows_per_group)
 
 
 class _MultiLinearBnRelu(torch.autograd.Function):
@@ -736,7 +761,7 @@ def gemm_splits(M, N, K):
 
 
 def gemm_bf16(a, b, a_mn=False, b_mn=False, bias=None, out=None, out_dtype=torch.bfloat16, splits=1,
-              stats=False, tile_n=0, ctas=0):
+              stats=False, tile_n=0, ctas=0, bias_rows=None, rows_per_group=0):
     """K6: out[M,N] (+bias) = A . B^T on tcgen05 tensor cores (bf16 operands, fp32 accumulate).
 
     a: (M,K) [a_mn=False] or (K,M) [a_mn=True];  b: (N,K) [b_mn=False] or (K,N) [b_mn=True]; both bf16
@@ -762,8 +787,13 @@ def gemm_bf16(a, b, a_mn=False, b_mn=False, bias=None, out=None, out_dtype=torch
         st = torch.empty((M + 127) // 128, 2, N, dtype=torch.float32, device=a.device) if stats else None
         if bias is not None:
             bias = _need(bias, torch.float32, "bias")
+        if bias_rows is not None:
+            bias_rows = _need(bias_rows, torch.float32, "bias_rows")
+            if bias_rows.shape != ((M + rows_per_group - 1) // rows_per_group, N):
+                raise ValueError("gemm_bf16: bias_rows must be (ceil(M / rows_per_group), N)")
         _call("hsp_gemm_bf16", _p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), M, N, K,
-              _p(bias), _p(buf), ldo, int(f32), splits, _p(st), tile_n, ctas, _stream())
+              _p(bias), _p(bias_rows), int(rows_per_group), _p(buf), ldo, int(f32), splits, _p(st), tile_n, ctas,
+              _stream())
     res = buf
     if splits > 1:
         res = buf[0] if splits == 1 else buf.sum(dim=0)
@@ -880,6 +910,25 @@ def fused_losses(weights, face, recon, p_green, p_red, f_green, f_red, pred_T, p
     terms = _FusedLosses.apply(tuple(float(x) for x in weights), face, recon, p_green, p_red, f_green, f_red,
                                pred_T, pred_s, PC, gt_R, gt_t, gt_s, mean_shape, sym, obj_id)
     return {name: terms[i] for i, name in enumerate(LOSS_TERMS)}
+
+
+# ------------------------------------------------------------ K10: augmentation
+def augment(PC, R, t, s, mean_shape, sym, aug_bb, aug_rt_t, aug_rt_r, model_point, nocs_scale, obj_id, gates, ey,
+            defor, probs, pc_r):
+    """HSPose.data_augment as one launch -> (PC, R, t, s).  gates (B,4), ey (B,2), defor (B,N,3): the uniform
+    draws; probs = (aug_bb_pro, aug_rt_pro, aug_bc_pro, aug_pc_pro)."""
+    args = [_need(x.float() if x.dtype != torch.float32 else x, torch.float32, n) for x, n in
+            ((PC, "PC"), (R, "R"), (t, "t"), (s, "s"), (mean_shape, "mean_shape"), (sym, "sym"), (aug_bb, "aug_bb"),
+             (aug_rt_t, "aug_rt_t"), (aug_rt_r, "aug_rt_r"), (model_point, "model_point"), (nocs_scale, "nocs_scale"),
+             (obj_id, "obj_id"), (gates, "gates"), (ey, "ey"), (defor, "defor"))]
+    B, N, _ = PC.shape
+    f = ctypes.c_float
+    with torch.cuda.device(PC.device):
+        PC_o, R_o = torch.empty_like(args[0]), torch.empty_like(args[1])
+        t_o, s_o = torch.empty_like(args[2]), torch.empty_like(args[3])
+        _call("hsp_augment", *[_p(a) for a in args], f(probs[0]), f(probs[1]), f(probs[2]), f(probs[3]), f(pc_r),
+              B, N, model_point.shape[1], _p(PC_o), _p(R_o), _p(t_o), _p(s_o), _stream())
+    return PC_o, R_o, t_o, s_o
 
 
 # ---------------------------------------------------------------- chamfer

@@ -261,14 +261,18 @@ int hsp_bn_apply_fwd(const void* x, int ldx, int M, int C, int dtype, const floa
  *   stats (optional, bf16 output): (ceil(M/128), 2, N) floats — per 128-row block the column
  *     sums and sums of squares of the values AS STORED; this is the partial layout
  *     hsp_bn_apply_fwd() consumes, so BatchNorm needs no statistics pass of its own.
+ *   bias_rows (optional, (ceil(M/rows_per_group), N) floats, N % 4 == 0): a second bias shared by groups of
+ *     rows_per_group consecutive rows — the per-object `f_global` block of face_head[0]
+ *     (FaceRecon.py:118-121: cat[f_global repeated over the points, ...]) as a broadcast term.
  *   tile_n in {64,128,256} and ctas in {1,2} pick the tile (0 = library default).            */
 int hsp_gemm_bf16_splits(int M, int N, int K, int out_f32);
 /* Diagnostics for profiling (results are WRONG while non-zero): bit 0 skips the epilogue's staging
  * writes and stores, bit 1 the MMAs, bit 2 the TMA loads.  Returns the previous value.          */
 int hsp_gemm_debug(int flags);
 int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major,
-                  int M, int N, int K, const float* bias, void* out, int ldo, int out_f32,
-                  int splits, float* stats, int tile_n, int ctas, void* stream);
+                  int M, int N, int K, const float* bias, const float* bias_rows, int rows_per_group,
+                  void* out, int ldo, int out_f32, int splits, float* stats, int tile_n, int ctas,
+                  void* stream);
 
 /* ------------------------------------------------------------------ K8 ---
  * The 19-term loss graph of training stage 'PoseNet_only' (L1 loss type), forward and backward:
@@ -314,6 +318,19 @@ int hsp_optim_step(int kind, float* param, const float* grad, float* exp_avg, fl
                    const float* lr, float beta1, float beta2, float eps, float weight_decay,
                    float clip_max_norm, float alpha, int k, int nsma_threshold, float* grad_norm_out,
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ K10 --
+ * HSPose.data_augment (network/HSPose.py:185-256 over datasets/data_augmentation.py:70-79,106-127,134-140,
+ * 183-190) as one launch: Bernoulli-gated box scaling, rigid perturbation, bowl/mug taper, point noise.
+ * Random inputs (uniform [0,1), drawn by the caller in the reference's order): gates (B,4) = [bb, rt, bc, pc],
+ * ey (B,2) = [up, down], defor (B,N,3).  p_* = FLAGS.aug_*_pro, pc_r = FLAGS.aug_pc_r.
+ * R (B,3,3) row-major, model_point (B,Nm,3).  Outputs: PC_out (B,N,3), R_out, t_out, s_out (B,3).      */
+int hsp_augment(const float* PC, const float* R, const float* t, const float* s, const float* mean_shape,
+                const float* sym, const float* aug_bb, const float* aug_rt_t, const float* aug_rt_r,
+                const float* model_point, const float* nocs_scale, const float* obj_id,
+                const float* gates, const float* ey, const float* defor, float p_bb, float p_rt,
+                float p_bc, float p_pc, float pc_r, int B, int N, int Nm, float* PC_out, float* R_out,
+                float* t_out, float* s_out, void* stream);
 
 #ifdef __cplusplus
 }

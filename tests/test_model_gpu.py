@@ -467,3 +467,30 @@ def test_fused_loss_kernel_matches_loss_modules(cuda):
             rel = 1e-3 if gname == "recon" and name in ("face", "Pred_T") else 5e-5
             err = (ga - gb).abs().max().item()
             assert err <= rel * ga.abs().max().item() + 1e-9, (gname, name, err, ga.abs().max().item())
+
+
+@pytest.mark.parametrize("tag,probs", [
+    ("all", dict(aug_pc_pro=1.0, aug_rt_pro=1.0, aug_bb_pro=1.0, aug_bc_pro=1.0)),
+    ("default", dict(aug_pc_pro=0.2, aug_rt_pro=0.3, aug_bb_pro=0.3, aug_bc_pro=0.3))])
+def test_augment_kernel_matches_reference(cuda, golden, tag, probs):
+    """K10 (csrc/augment.cu) against goldens of the REFERENCE's HSPose.data_augment (network/HSPose.py:185-256),
+    fed the same uniform draws the reference consumed (CPU generator, seed 777, same order and shapes)."""
+    import hspose_b200.ops as ops
+    g = golden("aug")
+    b = synth_batch(8, 1028, seed=5, train=True)
+    torch.manual_seed(777)
+    bs = 8
+    g_bb, g_rt, g_bc = (torch.rand((bs, 1)) for _ in range(3))
+    ey_up, ey_down = torch.rand((bs, 1)), torch.rand((bs, 1))
+    g_pc = torch.rand((bs, 1))
+    defor = torch.rand(b["PC"].shape)
+    d = {k: v.to(cuda) for k, v in b.items()}
+    PC, R, t, s = ops.augment(d["PC"], d["gt_R"], d["gt_t"], d["gt_s"], d["mean_shape"], d["sym"], d["aug_bb"],
+                              d["aug_rt_t"], d["aug_rt_r"], d["model_point"], d["nocs_scale"], d["obj_id"],
+                              torch.cat([g_bb, g_rt, g_bc, g_pc], 1).to(cuda), torch.cat([ey_up, ey_down], 1).to(cuda),
+                              defor.to(cuda), (probs["aug_bb_pro"], probs["aug_rt_pro"], probs["aug_bc_pro"],
+                                               probs["aug_pc_pro"]), 0.2)
+    np.testing.assert_allclose(PC.cpu().numpy(), g[f"{tag}_PC"], atol=2e-6)
+    np.testing.assert_allclose(R.cpu().numpy(), g[f"{tag}_R"], atol=1e-6)
+    np.testing.assert_allclose(t.cpu().numpy(), g[f"{tag}_t"], atol=1e-6)
+    np.testing.assert_allclose(s.cpu().numpy(), g[f"{tag}_s"], atol=1e-6)
