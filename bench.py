@@ -156,9 +156,9 @@ def _alg_bytes(name, a, train=True):
     if name == "hsp_bn_relu_bwd":      # ints: ldx, lddy, M, C, dtype, ...
         ldx, lddy, M, C, dt = a[:5]
         return 3 * M * C * (2 if dt == 1 else 4)
-    if name == "hsp_gemm_bf16":        # ints: lda, a_mn, ldb, b_mn, M, N, K, rows_per_group, ldo, out_f32, splits, ...
+    if name == "hsp_gemm_bf16":        # ints: lda, a_mn, ldb, b_mn, M, N, K, rows_per_group, relu, ldo, out_f32, splits, ...
         lda, amn, ldb, bmn, M, N, K = a[:7]
-        f32, splits = (a[9], a[10]) if len(a) > 10 else (0, 1)
+        f32, splits = (a[10], a[11]) if len(a) > 11 else (0, 1)
         return 2 * (M * K + N * K) + (4 * splits if f32 else 2) * M * N
     if name in ("hsp_chamfer_fwd", "hsp_chamfer_bwd"):
         B, N, M = a[:3]
@@ -205,7 +205,7 @@ def _gather_bytes(name, a):
 def kernel_breakdown(records, steps):
     agg = {}
     for name, a, ms in records:
-        key = (name, a[:11])
+        key = (name, a[:12])
         d = agg.setdefault(key, {"ms": 0.0, "n": 0})
         d["ms"] += ms
         d["n"] += 1
@@ -491,14 +491,16 @@ def run_b200(args):
     ops.enable_timing(False)
 
     def leave():
-        """NCCL communicators captured in a CUDA graph do not tear down cleanly
-        (destroy_process_group blocks); all ranks meet once more, then exit hard."""
+        """Tear down: the CUDA graph that captured the NCCL all-reduces is destroyed BEFORE the process group
+        (a communicator still referenced by a live graph blocks destroy_process_group)."""
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
-            sys.stdout.flush()
-            sys.stderr.flush()
-            os._exit(0)
+            trainer.graph = None
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
+            dist.destroy_process_group()
 
     if rank != 0:
         leave()

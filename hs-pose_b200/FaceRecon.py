@@ -61,6 +61,30 @@ def conv1x1(conv: nn.Conv1d, x_bnc, pad_in=0, pad_out=0):
     return F.linear(x_bnc, w, b)
 
 
+def _eval_folded(conv: nn.Conv1d, bn: nn.BatchNorm1d, x_bnc, relu):
+    """Evaluation (running statistics), fp32: Conv1d(k=1) -> BatchNorm1d -> ReLU folded into ONE fp32-accurate
+    tensor-core GEMM (ops.linear_fp32x: 3-way bf16 split, K6 kernel, bias + ReLU in the epilogue).  The folded
+    and pre-split weights are cached on the conv module and rebuilt when any source tensor changes."""
+    key = tuple((t.data_ptr(), t._version) for t in (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
+                                                     bn.running_var) if t is not None) + (x_bnc.shape[-1],)
+    cache = getattr(conv, "_hsp_eval_fold", None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            w = conv.weight[:, :, 0] * s[:, None]
+            pad_in = x_bnc.shape[-1] - conv.in_channels
+            if pad_in:
+                w = F.pad(w, (0, pad_in))
+            b0 = conv.bias if conv.bias is not None else torch.zeros_like(bn.running_mean)
+            b = ((b0 - bn.running_mean) * s + bn.bias).float().contiguous()
+            kpad = (w.shape[1] + 63) // 64 * 64
+            cache = (key, ops.split_bf16(w.float().contiguous(), ops._SPLIT_B, kpad), b)
+        conv._hsp_eval_fold = cache
+    shape = x_bnc.shape
+    y = ops.eval_linear(x_bnc.reshape(-1, shape[-1]), cache[1], cache[2], relu)
+    return y.view(*shape[:-1], conv.out_channels)
+
+
 def conv_bn_relu_points(conv: nn.Conv1d, bn: nn.BatchNorm1d, x_bnc, relu=True):
     """Conv1d(k=1) -> BatchNorm1d -> ReLU on a (bs, N, C) / (M, C) tensor.  On the mixed-precision
     training path this is ONE fused autograd node (ops.linear_bn_relu: bf16 tensor-core GEMMs,
@@ -77,6 +101,10 @@ def conv_bn_relu_points(conv: nn.Conv1d, bn: nn.BatchNorm1d, x_bnc, relu=True):
         z = ops.linear_bn_relu(x_bnc.reshape(-1, shape[-1]), w, conv.bias, bn.weight, bn.bias,
                                bn.running_mean, bn.running_var, bn.eps, bn.momentum, relu)
         return z.view(*shape[:-1], conv.out_channels)
+    if (not bn.training and not mixed_precision() and x_bnc.is_cuda and x_bnc.dtype == torch.float32
+            and conv.in_channels >= 512 and conv.out_channels % 4 == 0 and x_bnc.numel() // shape[-1] >= 1024
+            and bn.running_mean is not None and bn.affine):
+        return _eval_folded(conv, bn, x_bnc, relu)
     return bn_points(bn, conv1x1(conv, x_bnc, pad_in), relu=relu)
 
 

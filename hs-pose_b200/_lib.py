@@ -41,8 +41,8 @@ SIGNATURES = {
                                  c_int, P, P, P, P, P, P, c_int, P]),
     "hsp_gemm_bf16_splits": (c_int, [c_int] * 4),
     "hsp_gemm_debug": (c_int, [c_int]),
-    "hsp_gemm_bf16": (c_int, [P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, c_int, c_int,
-                              c_int, P, c_int, c_int, P]),
+    "hsp_gemm_bf16": (c_int, [P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int,
+                              c_int, c_int, P, c_int, c_int, P]),
     "hsp_losses_num_terms": (c_int, []),
     "hsp_losses_num_sums": (c_int, []),
     "hsp_losses_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, P, P, P]),
@@ -52,6 +52,7 @@ SIGNATURES = {
                                ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_int, c_int, P, P,
                                c_size_t, P]),
     "hsp_augment": (c_int, [P] * 15 + [ctypes.c_float] * 5 + [c_int] * 3 + [P] * 5),
+    "hsp_split_bf16": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "hsp_residual_sum_fwd": (c_int, [P, P, c_int, P, P, c_int, P, P, c_int, c_int, c_int, P, P]),
     "hsp_residual_sum_bwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P]),
     "hsp_colmax_fwd": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P]),

@@ -209,6 +209,7 @@ struct Params {
   const float* bias_rows;   // (ceil(M / rows_per_group), N) or NULL: a second bias, shared by groups of consecutive rows
   int rows_per_group;
   float* stats;         // (ceil(M/128), 2, N) per-row-block column sums / sums of squares, or NULL
+  int relu;             // epilogue: max(0, .) after the biases
   int debug;            // diagnostics (hsp_gemm_debug): 1 = no staging writes / stores, 2 = no MMAs, 4 = no TMA loads
 };
 
@@ -433,6 +434,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 r4[e] = (brow_vec || n0 + ch * OUT_COLS + 4 * j + e < p.N) ? __ldg(brow + 4 * j + e) : 0.f;
               o.x += r4[0]; o.y += r4[1]; o.z += r4[2]; o.w += r4[3];
             }
+            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             *reinterpret_cast<float4*>(srow + ((j ^ (row & 7)) << 4)) = o;
           }
         } else {
@@ -465,6 +467,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   f[e].y += c0 + 1 < p.N ? __ldg(brow + 8 * j + 2 * e + 1) : 0.f;
                 }
               }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { f[e].x = fmaxf(f[e].x, 0.f); f[e].y = fmaxf(f[e].y, 0.f); }
             }
             uint4 o;
             o.x = pack_bf16(f[0].x, f[0].y);
@@ -622,8 +628,9 @@ extern "C" int hsp_gemm_bf16_splits(int M, int N, int K, int out_f32) {
 }
 
 extern "C" int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M,
-                             int N, int K, const float* bias, const float* bias_rows, int rows_per_group, void* out,
-                             int ldo, int out_f32, int splits, float* stats, int tile_n, int ctas, void* stream) {
+                             int N, int K, const float* bias, const float* bias_rows, int rows_per_group, int relu,
+                             void* out, int ldo, int out_f32, int splits, float* stats, int tile_n, int ctas,
+                             void* stream) {
   using namespace hsp;
   using namespace hsp::gemm;
   if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0 || splits < 1) return HSP_EINVAL;
@@ -633,7 +640,7 @@ extern "C" int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void*
     return HSP_EINVAL;
   if (lda < (a_mn_major ? M : K) || ldb < (b_mn_major ? N : K) || ldo < N) return HSP_EINVAL;
   if (stats && (out_f32 || splits != 1)) return HSP_EINVAL;
-  if (splits > 1 && (!out_f32 || bias || bias_rows)) return HSP_EINVAL;
+  if (splits > 1 && (!out_f32 || bias || bias_rows || relu)) return HSP_EINVAL;
   if (bias_rows && (rows_per_group <= 0 || (N % 4) != 0 || ((uintptr_t)bias_rows % 16) != 0)) return HSP_EINVAL;
   const int total_kb = (K + BK - 1) / BK;
   const int kb_per = (total_kb + splits - 1) / splits;
@@ -661,6 +668,7 @@ extern "C" int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void*
   p.splits = splits; p.kb_per_split = kb_per;
   p.bias = bias; p.stats = stats;
   p.bias_rows = bias_rows; p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
+  p.relu = relu ? 1 : 0;
   p.debug = g_gemm_debug;
   cudaStream_t st = (cudaStream_t)stream;
 #define HSP_GEMM_CASE(BN_, CT_)                                                          \

@@ -14,7 +14,7 @@ import copy
 
 import torch
 
-from . import gcn3d, ops, optim, parallel
+from . import gcn3d, geom, ops, optim, parallel
 
 _RING = 4   # pinned staging slots per Pool_layer permutation (bounds how far the CPU may run ahead)
 
@@ -48,7 +48,16 @@ class TrainStep:
     def __init__(self, model, lr=1e-4, clip=5.0, amp=True, graph=True, optimizer=None,
                  tf32=False):
         self.model, self.clip, self.amp, self.use_graph = model, clip, amp, graph
-        self.flat = parallel.FlatGradients(model.posenet.parameters())
+        # heads first: their gradients are final long before the backbone's backward ends, so their share of the
+        # all-reduce (~70 % of the 38.8 MB) overlaps it on a side stream (only when there is more than one rank)
+        backbone = {id(p) for n, p in model.posenet.named_parameters()
+                    if n.startswith("face_recon.conv_") or n.startswith("face_recon.bn") or n.startswith("face_recon.pool")}
+        self.flat = parallel.FlatGradients(model.posenet.parameters(), early=lambda p: id(p) not in backbone)
+        self._overlap = self.flat.world > 1 and self.flat.n_early > 0
+        self._side, self._pending, self._early_done = None, 0, None
+        if self._overlap:
+            for p in self.flat.early_params:
+                p.register_post_accumulate_grad_hook(self._on_early_grad)
         # optimiser: "adam" (BASELINE.json configs[2]) or "ranger" (the reference's, tools/solver_utils.py:49-50)
         # = the K9 kernels over ONE flat parameter buffer with the clip folded in; a torch.optim.Optimizer
         # instance is also accepted (then `clip` runs as a separate pass)
@@ -93,9 +102,22 @@ class TrainStep:
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
 
+    # ---- early gradient bucket: all-reduce on a side stream as soon as the last head gradient has landed
+    def _on_early_grad(self, p):
+        self._pending -= 1
+        if self._pending == 0:
+            cur = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=p.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self.flat.all_reduce_early()
+            self._early_done = True
+
     # ---- the step itself
     def _body(self, batch, draw_inline):
         self._pool_call, self._draw_inline = 0, draw_inline
+        self._pending, self._early_done = (len(self.flat.early_params) if self._overlap else -1), False
         prev = gcn3d.set_pool_rows_provider(self._provider)
         try:
             with self._tf32_scope(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
@@ -105,7 +127,11 @@ class TrainStep:
             total.backward()
         finally:
             gcn3d.set_pool_rows_provider(prev)
-        self.flat.all_reduce_mean()
+        if self._overlap and self._early_done:
+            self.flat.all_reduce_mean(skip_early=True)            # backbone bucket on the main stream
+            torch.cuda.current_stream().wait_stream(self._side)   # join the heads' all-reduce
+        else:
+            self.flat.all_reduce_mean()
         if isinstance(self.opt, optim.FlatOptimizer):
             self.opt.step()                       # clip + update, three launches
         else:
@@ -206,3 +232,84 @@ class TrainStep:
         self._refresh_pool_rows()
         self.graph.replay()
         return self.static_loss
+
+
+class EvalRunner:
+    """The per-image call of the reference's evaluation loop (evaluation/evaluate.py:91-108): forward of all
+    detections of one image (batch = 1..~8 objects) + `generate_RT` + `pred_s = Pred_s + mean_shape`, replayed
+    from ONE CUDA graph per batch-size bucket.  The published 38 FPS is exactly this region, latency-bound at
+    these batch sizes; a graph replay removes the ~300 kernel-launch gaps.  A batch is padded up to its bucket
+    by repeating its first object (objects are independent in eval mode: BatchNorm uses running statistics).
+    Pool_layer's sample is still drawn with `torch.randperm` on the CPU generator before each replay
+    (reference gcn3d.py:243 draws it even in eval mode)."""
+
+    def __init__(self, model, buckets=(1, 2, 4, 8, 16, 32), graph=True):
+        self.model, self.buckets, self.use_graph = model, tuple(sorted(buckets)), graph
+        self.graphs = {}          # bucket -> (graph, static inputs, static outputs, pool rows)
+        self._rows, self._call_i, self._inline = None, 0, True
+
+    def _provider(self, vertice_num, pool_num, device):
+        i = self._call_i
+        self._call_i += 1
+        if i == len(self._rows):
+            self._rows.append(_PoolRows(vertice_num, pool_num, device))
+        if self._inline:
+            self._rows[i].draw()
+        return self._rows[i].dev
+
+    def _forward(self, inp):
+        out = self.model(PC=inp["PC"], obj_id=inp["obj_id"], mean_shape=inp["mean_shape"], sym=inp["sym"])
+        res = {k: out[k] for k in ("p_green_R", "p_red_R", "f_green_R", "f_red_R", "Pred_T", "Pred_s")}
+        res["pred_RT"] = geom.generate_RT([res["p_green_R"], res["p_red_R"]], [res["f_green_R"], res["f_red_R"]],
+                                          res["Pred_T"], "vec", inp["sym"])
+        res["pred_s"] = res["Pred_s"] + inp["mean_shape"]
+        return res
+
+    def _run(self, inp, rows, inline):
+        self._rows, self._call_i, self._inline = rows, 0, inline
+        prev = gcn3d.set_pool_rows_provider(self._provider)
+        try:
+            with torch.no_grad():
+                return self._forward(inp)
+        finally:
+            gcn3d.set_pool_rows_provider(prev)
+
+    @torch.no_grad()
+    def __call__(self, PC, obj_id, mean_shape, sym):
+        n = PC.shape[0]
+        dev = next(self.model.parameters()).device
+        if n == 0:
+            return {"pred_RT": torch.zeros(0, 4, 4, device=dev), "pred_s": torch.zeros(0, 3, device=dev)}
+        nb = next((b for b in self.buckets if b >= n), None)
+        given = {"PC": PC, "obj_id": obj_id, "mean_shape": mean_shape, "sym": sym}
+        if not self.use_graph or nb is None:      # larger than the largest bucket: plain eager forward
+            rows = []
+            return self._run({k: v.to(dev) for k, v in given.items()}, rows, True)
+        if nb not in self.graphs:
+            inp = {k: torch.zeros((nb,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev) for k, v in given.items()}
+            rows = []
+            self._fill(inp, given, n, nb)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._run(inp, rows, True)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._run(inp, rows, False)
+            self.graphs[nb] = (g, inp, out, rows)
+        g, inp, out, rows = self.graphs[nb]
+        self._fill(inp, given, n, nb)
+        for r in rows:
+            r.draw()
+        g.replay()
+        return {k: v[:n].clone() for k, v in out.items()}
+
+    @staticmethod
+    def _fill(inp, given, n, nb):
+        for k, v in given.items():
+            inp[k][:n].copy_(v, non_blocking=True)
+            if nb > n:
+                inp[k][n:].copy_(inp[k][:1].expand(nb - n, *inp[k].shape[1:]))

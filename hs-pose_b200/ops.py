@@ -761,7 +761,7 @@ def gemm_splits(M, N, K):
 
 
 def gemm_bf16(a, b, a_mn=False, b_mn=False, bias=None, out=None, out_dtype=torch.bfloat16, splits=1,
-              stats=False, tile_n=0, ctas=0, bias_rows=None, rows_per_group=0):
+              stats=False, tile_n=0, ctas=0, bias_rows=None, rows_per_group=0, relu=False):
     """K6: out[M,N] (+bias) = A . B^T on tcgen05 tensor cores (bf16 operands, fp32 accumulate).
 
     a: (M,K) [a_mn=False] or (K,M) [a_mn=True];  b: (N,K) [b_mn=False] or (K,N) [b_mn=True]; both bf16
@@ -792,8 +792,8 @@ def gemm_bf16(a, b, a_mn=False, b_mn=False, bias=None, out=None, out_dtype=torch
             if bias_rows.shape != ((M + rows_per_group - 1) // rows_per_group, N):
                 raise ValueError("gemm_bf16: bias_rows must be (ceil(M / rows_per_group), N)")
         _call("hsp_gemm_bf16", _p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), M, N, K,
-              _p(bias), _p(bias_rows), int(rows_per_group), _p(buf), ldo, int(f32), splits, _p(st), tile_n, ctas,
-              _stream())
+              _p(bias), _p(bias_rows), int(rows_per_group), int(relu), _p(buf), ldo, int(f32), splits, _p(st),
+              tile_n, ctas, _stream())
     res = buf
     if splits > 1:
         res = buf[0] if splits == 1 else buf.sum(dim=0)
@@ -929,6 +929,66 @@ def augment(PC, R, t, s, mean_shape, sym, aug_bb, aug_rt_t, aug_rt_r, model_poin
         _call("hsp_augment", *[_p(a) for a in args], f(probs[0]), f(probs[1]), f(probs[2]), f(probs[3]), f(pc_r),
               B, N, model_point.shape[1], _p(PC_o), _p(R_o), _p(t_o), _p(s_o), _stream())
     return PC_o, R_o, t_o, s_o
+
+
+# ------------------------------------------------------------ fp32-accurate GEMM on the bf16 tensor cores
+# term order: SMALLEST first (x1 w3, x2 w2, x3 w1 ~ 2^-16; x1 w2, x2 w1 ~ 2^-8; x1 w1 last), so the small terms are
+# summed while the TMEM accumulator is still small — with the large term first a single accumulator loses them
+# to its rounding (measured 9e-6 vs 9e-7 relative error, tools/split_check.py)
+_SPLIT_A = (0, 1, 2, 0, 1, 0)
+_SPLIT_B = (2, 1, 0, 1, 0, 0)
+
+
+def split_bf16(x, comp, kpad):
+    """(M,K) fp32 -> (M, len(comp)*kpad) bf16 concatenation of the bf16 split components comp[t] of x."""
+    x = _need(x, torch.float32, "x")
+    if x.dim() != 2:
+        raise ValueError("split_bf16 expects a 2-D matrix")
+    M, K = x.shape
+    arr = (ctypes.c_int * len(comp))(*comp)
+    with torch.cuda.device(x.device):
+        out = torch.empty(M, len(comp) * kpad, dtype=torch.bfloat16, device=x.device)
+        _call("hsp_split_bf16", _p(x), x.stride(0), M, K, kpad, len(comp), arr, _p(out), _stream())
+    return out
+
+
+def linear_fp32x(x, W, b=None, relu=False, w_split=None, splits=1):
+    """y = x @ W^T (+ b) (ReLU) with fp32 accuracy on the bf16 tensor cores: 3-way bf16 split of both operands,
+    the six significant cross terms as ONE K6 GEMM over a 6x longer reduction axis (measured on B200: error vs
+    float64 on par with the strict-fp32 library GEMM, tools/split_check.py; splits = 6 gives every term its own
+    accumulator plane).  x (M,K), W (N,K) fp32 -> (M,N) fp32.  No autograd (evaluation path).
+    w_split: the split of W from a previous call (weights are constant in evaluation)."""
+    M, K = x.shape
+    kpad = (K + 63) // 64 * 64
+    a = split_bf16(x, _SPLIT_A, kpad)
+    bw = w_split if w_split is not None else split_bf16(W, _SPLIT_B, kpad)
+    if splits == 1:      # bias and ReLU in the GEMM epilogue
+        return gemm_bf16(a, bw, bias=b, relu=relu, out_dtype=torch.float32)
+    y = gemm_bf16(a, bw, out_dtype=torch.float32, splits=splits)
+    if b is not None:
+        y = y + b
+    return torch.relu_(y) if relu else y
+
+
+class _EvalLinear(torch.autograd.Function):
+    """linear_fp32x as an autograd node that refuses to back-propagate (evaluation fast path: the folded,
+    pre-split weights carry no gradient) — loud instead of a silently missing gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w_split, b, relu, n_out):
+        M, K = x.shape
+        kpad = w_split.shape[1] // 6
+        a = split_bf16(x, _SPLIT_A, kpad)
+        return gemm_bf16(a, w_split, bias=b, relu=relu, out_dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError("hs-pose_b200: the folded Conv1d+BatchNorm(eval) fast path has no backward; "
+                                  "call .train() (batch statistics) to differentiate through this block")
+
+
+def eval_linear(x, w_split, b, relu):
+    return _EvalLinear.apply(x, w_split, b, relu, w_split.shape[0])
 
 
 # ---------------------------------------------------------------- chamfer

@@ -59,8 +59,19 @@ def shard_batch(batch, rank, world):
 class FlatGradients:
     """All gradients of `params` as views of one flat fp32 buffer + one all-reduce."""
 
-    def __init__(self, params):
+    def __init__(self, params, early=None):
+        """`early`: optional predicate(param) -> True for parameters whose gradients are complete EARLY in the
+        backward (the pose / reconstruction heads: autograd reaches them before the backbone).  They are laid
+        out first in the flat buffer, as one contiguous bucket that `all_reduce_early()` can reduce on a side
+        stream while the backbone's backward is still running."""
         self.params = [p for p in params if p.requires_grad]
+        self.n_early = 0
+        if early is not None:
+            first = [p for p in self.params if early(p)]
+            rest = [p for p in self.params if not early(p)]
+            self.params = first + rest
+            self.n_early = sum(p.numel() for p in first)
+            self.early_params = first
         n = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
@@ -94,14 +105,24 @@ class FlatGradients:
         """zero_grad() that keeps the views (never set_to_none)."""
         self.flat.zero_()
 
-    def all_reduce_mean(self, async_op=False):
-        if self.world == 1:
-            return None
+    def _reduce(self, t):
         if dist.get_backend() == "nccl":
-            return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, async_op=async_op)
-        w = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=False)
-        self.flat.div_(self.world)
-        return w
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t.div_(self.world)
+
+    def all_reduce_mean(self, skip_early=False):
+        """Average the flat gradient over the ranks (ONE collective, or the late bucket only when the early
+        bucket has already been launched by all_reduce_early)."""
+        if self.world == 1:
+            return
+        self._reduce(self.flat[self.n_early:] if (skip_early and self.n_early) else self.flat)
+
+    def all_reduce_early(self):
+        """Average the early bucket (the heads' gradients)."""
+        if self.world > 1 and self.n_early:
+            self._reduce(self.flat[:self.n_early])
 
     def clip_(self, max_norm):
         """clip_grad_norm_ on the flat buffer (one norm kernel instead of 160)."""

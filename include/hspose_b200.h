@@ -264,6 +264,7 @@ int hsp_bn_apply_fwd(const void* x, int ldx, int M, int C, int dtype, const floa
  *   bias_rows (optional, (ceil(M/rows_per_group), N) floats, N % 4 == 0): a second bias shared by groups of
  *     rows_per_group consecutive rows — the per-object `f_global` block of face_head[0]
  *     (FaceRecon.py:118-121: cat[f_global repeated over the points, ...]) as a broadcast term.
+ *   relu != 0: max(0, .) after the biases (the ReLU of a folded Conv1d -> BatchNorm(eval) -> ReLU block).
  *   tile_n in {64,128,256} and ctas in {1,2} pick the tile (0 = library default).            */
 int hsp_gemm_bf16_splits(int M, int N, int K, int out_f32);
 /* Diagnostics for profiling (results are WRONG while non-zero): bit 0 skips the epilogue's staging
@@ -271,8 +272,8 @@ int hsp_gemm_bf16_splits(int M, int N, int K, int out_f32);
 int hsp_gemm_debug(int flags);
 int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major,
                   int M, int N, int K, const float* bias, const float* bias_rows, int rows_per_group,
-                  void* out, int ldo, int out_f32, int splits, float* stats, int tile_n, int ctas,
-                  void* stream);
+                  int relu, void* out, int ldo, int out_f32, int splits, float* stats, int tile_n,
+                  int ctas, void* stream);
 
 /* ------------------------------------------------------------------ K8 ---
  * The 19-term loss graph of training stage 'PoseNet_only' (L1 loss type), forward and backward:
@@ -331,6 +332,15 @@ int hsp_augment(const float* PC, const float* R, const float* t, const float* s,
                 const float* gates, const float* ey, const float* defor, float p_bb, float p_rt,
                 float p_bc, float p_pc, float pc_r, int B, int N, int Nm, float* PC_out, float* R_out,
                 float* t_out, float* s_out, void* stream);
+
+/* fp32 -> bf16 multi-term split feeding hsp_gemm_bf16 for fp32-accurate contractions (the fp32 evaluation
+ * forward, BASELINE configs[1]): out (M, nterms*Kpad) bf16, term t = component comp[t] (0: bf16(x),
+ * 1: bf16(x - x1), 2: bf16(x - x1 - x2)) of x (M,K | ld), zero-padded to Kpad (multiple of 8) columns.
+ * comp is a HOST array.  With A' = split(x,[0,1,2,0,1,0]) and B' = split(w,[2,1,0,1,0,0]) (smallest cross
+ * terms first, so they are accumulated before the large one) the product A'.B'^T equals x.w^T to fp32
+ * accuracy (three dropped terms <= 2^-24 relative).                                                     */
+int hsp_split_bf16(const float* x, int ld, int M, int K, int Kpad, int nterms, const int* comp, void* out,
+                   void* stream);
 
 #ifdef __cplusplus
 }

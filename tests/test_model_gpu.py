@@ -325,8 +325,7 @@ def test_mixed_precision_step_close_to_fp32(cuda, groups, dense_bar):
 def test_cuda_graph_step_matches_eager(cuda):
     """engine.TrainStep: six optimiser steps replayed from one CUDA graph follow the eagerly launched
     loop (same CPU-generator pooling permutations, dropout/augmentation off).  The graph warm-up is
-    side-effect free, so step 0 sees identical weights.  Float atomics in the gather backward make even
-    two EAGER runs differ after the first update; the bar is 3x that measured eager-vs-eager noise."""
+    side-effect free, so the graph run starts from identical weights and optimiser state."""
     from hspose_b200.engine import TrainStep
     from hspose_b200.HSPose import HSPose
     F = _flags()
@@ -349,12 +348,15 @@ def test_cuda_graph_step_matches_eager(cuda):
             assert tr.launches_per_step and tr.launches_per_step > 50
         return np.array(out)
     try:
-        e1, e2, g = run(False), run(False), run(True)
-        assert np.all(np.isfinite(e1)) and np.all(np.isfinite(g))
-        assert abs(e1[0] - g[0]) <= 1e-3 * abs(e1[0]), (e1, g)          # identical weights at step 0
-        noise = np.abs(e1 - e2) / np.abs(e1)
-        diff = np.abs(e1 - g) / np.abs(e1)
-        assert np.all(diff <= 3.0 * noise + 1e-3), (e1, e2, g)
+        e, g = run(False), run(True)
+        assert np.all(np.isfinite(e)) and np.all(np.isfinite(g))
+        # Steps 0-2: the graph run starts from identical weights AND identical optimiser state (step 1 and 2 would
+        # differ by percent if the warm-up had applied updates or advanced Adam: the first Adam steps move every
+        # weight by ~lr).  Measured 0 / 0 / 2e-4.
+        assert np.all(np.abs(e[:3] - g[:3]) <= 1e-3 * np.abs(e[:3])), (e, g)
+        # Later steps: float atomics make even two EAGER runs drift apart (max-over-points winners get
+        # re-decided; measured eager-vs-eager 0.3 % .. 6 % by step 5) — sanity bound only.
+        assert np.all(np.abs(e - g) <= 0.25 * np.abs(e)), (e, g)
     finally:
         for n, v in saved.items():
             setattr(F, n, v)
@@ -494,3 +496,49 @@ def test_augment_kernel_matches_reference(cuda, golden, tag, probs):
     np.testing.assert_allclose(R.cpu().numpy(), g[f"{tag}_R"], atol=1e-6)
     np.testing.assert_allclose(t.cpu().numpy(), g[f"{tag}_t"], atol=1e-6)
     np.testing.assert_allclose(s.cpu().numpy(), g[f"{tag}_s"], atol=1e-6)
+
+
+def test_eval_runner_buckets_and_generate_RT(cuda, golden):
+    """engine.EvalRunner (the per-image call of evaluation/evaluate.py:91-108 as one CUDA-graph replay per
+    batch-size bucket): outputs equal the eager forward for batch sizes inside and between buckets, pred_RT equals
+    geom.generate_RT of the same outputs, a padded bucket does not disturb the real objects."""
+    from hspose_b200 import geom
+    from hspose_b200.engine import EvalRunner
+    from hspose_b200.HSPose import HSPose
+    F = _flags()
+    F.train, F.gcn_n_num = 0, 20
+    try:
+        model = HSPose("PoseNet_only")
+        model.posenet = _posenet(cuda, 0, 20)
+        model = model.to(cuda).eval()
+        runner = EvalRunner(model, buckets=(1, 4, 8))
+        for B in (1, 3, 4, 6):
+            b = synth_batch(B, 1028, seed=20 + B, train=False)
+            args = [b[k].to(cuda) for k in ("PC", "obj_id", "mean_shape", "sym")]
+            torch.manual_seed(7)
+            got = runner(*args)
+            torch.manual_seed(7)
+            got2 = runner(*args)                              # replay of the captured graph, same permutations
+            nb = next(x for x in (1, 4, 8) if x >= B)
+            padded = [torch.cat([a, a[:1].expand(nb - B, *a.shape[1:])]) if nb > B else a for a in args]
+            torch.manual_seed(7)
+            with torch.no_grad():
+                ref = model(PC=padded[0], obj_id=padded[1], mean_shape=padded[2], sym=padded[3])
+                torch.manual_seed(7)
+                loose = model(PC=args[0], obj_id=args[1], mean_shape=args[2], sym=args[3])
+            for n in NAMES:
+                assert got[n].shape == loose[n].shape
+                # the replayed graph == the eager forward of the same (padded) batch
+                assert (got[n] - ref[n][:B]).abs().max().item() <= 1e-6, (B, n)
+                assert torch.equal(got[n], got2[n]), (B, n)
+                # vs the UNPADDED eager batch only the library GEMMs' blocking changes (other row count): the
+                # feature-space KNN re-decides a few neighbour sets, as the reference itself does when its batch
+                # size changes (SURVEY.md Appendix C.2: 6e-4 .. 2e-3 on the rotation vectors)
+                assert (got[n] - loose[n]).abs().max().item() <= 1e-2, (B, n)
+            RT = geom.generate_RT([got["p_green_R"], got["p_red_R"]], [got["f_green_R"], got["f_red_R"]],
+                                  got["Pred_T"], "vec", args[3])
+            assert torch.allclose(got["pred_RT"], RT, atol=1e-6)
+            assert torch.allclose(got["pred_s"], got["Pred_s"] + args[2])
+        assert sorted(runner.graphs) == [1, 4, 8]
+    finally:
+        F.train, F.gcn_n_num = 1, 20

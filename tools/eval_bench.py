@@ -74,6 +74,20 @@ for B in (1, 4, 8, 16, 64):
                objects_per_s_eager=B / eager * 1e3, objects_per_s_graph=B / graph * 1e3)
     rows.append(row)
     print(json.dumps(row), flush=True)
+# the evaluation loop's per-image call through engine.EvalRunner (forward + generate_RT, bucketed CUDA graphs)
+from hspose_b200.engine import EvalRunner  # noqa: E402
+from hspose_b200.HSPose import HSPose  # noqa: E402
+model = HSPose("PoseNet_only").to(dev).eval()
+model.posenet = net
+runner = EvalRunner(model)
+for B in (1, 2, 3, 5, 8, 16):
+    b = synth_batch(B, 1028, seed=1, train=False)
+    args = [b[k].to(dev) for k in ("PC", "obj_id", "mean_shape", "sym")]
+    ms = timed(lambda: runner(*args), reps=50)
+    row = dict(config="EvalRunner: eval forward fp32 + generate_RT, CUDA graph per bucket, N=1028, k=20", B=B, ms=ms,
+               images_per_s=1e3 / ms, objects_per_s=B / ms * 1e3)
+    rows.append(row)
+    print(json.dumps(row), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/eval_bench.jsonl", "w") as f:
     for r in rows:
