@@ -104,12 +104,13 @@ class TrainStep:
 
     # ---- early gradient bucket: all-reduce on a side stream as soon as the last head gradient has landed
     def _on_early_grad(self, p):
+        # runs on an autograd worker thread, whose "current stream" is not the step's: fork from the stream
+        # the step itself runs on (recorded by _body; the capture stream in graph mode)
         self._pending -= 1
         if self._pending == 0:
-            cur = torch.cuda.current_stream()
             if self._side is None:
                 self._side = torch.cuda.Stream(device=p.device)
-            self._side.wait_stream(cur)
+            self._side.wait_stream(self._main)
             with torch.cuda.stream(self._side):
                 self.flat.all_reduce_early()
             self._early_done = True
@@ -118,6 +119,7 @@ class TrainStep:
     def _body(self, batch, draw_inline):
         self._pool_call, self._draw_inline = 0, draw_inline
         self._pending, self._early_done = (len(self.flat.early_params) if self._overlap else -1), False
+        self._main = torch.cuda.current_stream()
         prev = gcn3d.set_pool_rows_provider(self._provider)
         try:
             with self._tf32_scope(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):

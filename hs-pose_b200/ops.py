@@ -445,7 +445,7 @@ class _ConcatUpsample(torch.autograd.Function):
                 if not ctx.needs_input_grad[4 + i]:
                     grads.append(None)
                 elif bcast[i]:
-                    grads.append(gout[:, :, col:col + w].float().sum(dim=1))
+                    grads.append(gout[:, :, col:col + w].sum(dim=1, dtype=torch.float32))
                 else:
                     if nn is not None:
                         g = torch.zeros(B, nsrcs[i], w, dtype=torch.float32, device=gout.device)
@@ -839,7 +839,7 @@ class _LinearTC(torch.autograd.Function):
         dyb = _as_gemm_operand(dy)
         dx = gemm_bf16(dyb, Wb, b_mn=True) if ctx.needs_input_grad[0] else None
         dW = _wgrad(dyb, xb) if ctx.needs_input_grad[1] else None
-        db = dyb.float().sum(dim=0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        db = dyb.sum(dim=0, dtype=torch.float32) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return dx, dW, db
 
 

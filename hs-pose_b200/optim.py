@@ -39,8 +39,8 @@ class FlatOptimizer:
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.lr = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
-        off, ln, o = [], [], 0
-        for prm in flat.params:
+        off, ln = [], []
+        for prm, o in zip(flat.params, flat.offsets):
             n = prm.numel()
             if self.kind == RANGER and prm.dim() > 1:          # gradient centralisation per output row
                 rows, rl = prm.shape[0], n // prm.shape[0]
@@ -50,7 +50,6 @@ class FlatOptimizer:
                 for c in range(0, n, 1024):
                     off.append(o + c)
                     ln.append(-min(1024, n - c))
-            o += n
         self.seg_off = torch.tensor(off, dtype=torch.int32, device=dev)
         self.seg_len = torch.tensor(ln, dtype=torch.int32, device=dev)
         lib = _lib.load()

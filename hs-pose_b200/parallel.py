@@ -72,13 +72,19 @@ class FlatGradients:
             self.params = first + rest
             self.n_early = sum(p.numel() for p in first)
             self.early_params = first
-        n = sum(p.numel() for p in self.params)
+        # every parameter starts on a 16-byte boundary of the flat buffers (kernels read weights and write
+        # gradients with vector accesses); the few padding elements stay zero
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        n = off
+        if self.n_early:
+            self.n_early = self.offsets[len(self.early_params)] if len(self.early_params) < len(self.params) else n
         ref = self.params[0]
         self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.flat_param = None
 
@@ -89,14 +95,12 @@ class FlatGradients:
         multi-tensor launch group per 160 tensors.  Module parameters keep their identity, names and
         values (state_dict is unchanged); only their storage moves."""
         if self.flat_param is None:
-            flat = torch.empty_like(self.flat)
-            off = 0
+            flat = torch.zeros_like(self.flat)
             with torch.no_grad():
-                for p in self.params:
+                for p, off in zip(self.params, self.offsets):
                     n = p.numel()
                     flat[off:off + n].copy_(p.reshape(-1))
                     p.data = flat[off:off + n].view_as(p)
-                    off += n
             self.flat_param = torch.nn.Parameter(flat)
             self.flat_param.grad = self.flat
         return self.flat_param
