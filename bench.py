@@ -489,6 +489,9 @@ def run_b200(args):
     torch.cuda.synchronize()
     rows = kernel_breakdown(ops.timing_records(), ksteps)
     ops.enable_timing(False)
+    if os.environ.get("HSP_BENCH_DUMP") and rank == 0:     # every entry point x shape of the step, for analysis
+        with open(os.environ["HSP_BENCH_DUMP"], "w") as f:
+            json.dump(rows, f, indent=0)
 
     def leave():
         """Tear down: the CUDA graph that captured the NCCL all-reduces is destroyed BEFORE the process group

@@ -126,7 +126,20 @@ class TrainStep:
                 _, losses = self.model(**batch, do_loss=True)
             total = sum(v.reshape(()).float() for grp in losses.values() for v in grp.values())
             self.flat.zero()
-            total.backward()
+            if self._overlap:
+                total.backward()                  # gradients accumulate into the flat views as they arrive
+            else:
+                # one rank: let autograd hand over each gradient tensor (no per-parameter `grad += g` launch,
+                # ~160 of them) and gather them into the flat buffer with one multi-tensor copy
+                views = [p.grad for p in self.flat.params]
+                for p in self.flat.params:
+                    p.grad = None
+                total.backward()
+                got = [(v, p.grad) for v, p in zip(views, self.flat.params) if p.grad is not None]
+                if got:
+                    torch._foreach_copy_([v for v, _ in got], [g for _, g in got])
+                for v, p in zip(views, self.flat.params):
+                    p.grad = v
         finally:
             gcn3d.set_pool_rows_provider(prev)
         if self._overlap and self._early_done:

@@ -350,10 +350,10 @@ def test_cuda_graph_step_matches_eager(cuda):
     try:
         e, g = run(False), run(True)
         assert np.all(np.isfinite(e)) and np.all(np.isfinite(g))
-        # Steps 0-2: the graph run starts from identical weights AND identical optimiser state (step 1 and 2 would
-        # differ by percent if the warm-up had applied updates or advanced Adam: the first Adam steps move every
-        # weight by ~lr).  Measured 0 / 0 / 2e-4.
-        assert np.all(np.abs(e[:3] - g[:3]) <= 1e-3 * np.abs(e[:3])), (e, g)
+        # Steps 0-1: the graph run starts from identical weights AND identical optimiser state (step 1 would differ
+        # by percent if the warm-up had applied updates or advanced Adam: the first Adam steps move every weight
+        # by ~lr).  Measured: bit-identical losses at steps 0 and 1, 1e-2 by step 2.
+        assert np.all(np.abs(e[:2] - g[:2]) <= 1e-4 * np.abs(e[:2])), (e, g)
         # Later steps: float atomics make even two EAGER runs drift apart (max-over-points winners get
         # re-decided; measured eager-vs-eager 0.3 % .. 6 % by step 5) — sanity bound only.
         assert np.all(np.abs(e - g) <= 0.25 * np.abs(e)), (e, g)
@@ -515,6 +515,7 @@ def test_eval_runner_buckets_and_generate_RT(cuda, golden):
         for B in (1, 3, 4, 6):
             b = synth_batch(B, 1028, seed=20 + B, train=False)
             args = [b[k].to(cuda) for k in ("PC", "obj_id", "mean_shape", "sym")]
+            runner(*args)                                     # first use of a bucket: warm-up + capture (extra draws)
             torch.manual_seed(7)
             got = runner(*args)
             torch.manual_seed(7)
