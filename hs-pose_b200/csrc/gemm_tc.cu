@@ -62,6 +62,14 @@ struct Cfg {
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -214,7 +222,7 @@ struct Params {
 };
 
 // ---------------------------------------------------------------- the kernel
-template <int BN, int CTAS, bool OUT_F32>
+template <int BN, int CTAS, bool OUT_F32, bool EXTRA>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const Params p) {
@@ -410,14 +418,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int e = 0; e < NV; ++e) vc[e] = 0u;
         }
         // + bias, convert, write this thread's row into the 128-byte-swizzled staging tile
-        unsigned char* srow = so + row * 128;
         const float4* bs4 = reinterpret_cast<const float4*>(bs_tile + ch * OUT_COLS);
         const bool add_bias = p.bias != nullptr && (full_rows || row_ok);
-        // per-row-group bias (e.g. a per-object term broadcast over the object's points): this thread's row
+        // EXTRA instantiations only (kept out of the plain kernel: with four epilogue warps per SM every
+        // instruction of this loop is on the critical path of the output-bound shapes).  Per-row-group bias
+        // (e.g. a per-object term broadcast over the object's points) for this thread's row, then ReLU.
         const float* brow = nullptr;
-        if (p.bias_rows != nullptr && (full_rows || row_ok))
+        if (EXTRA && p.bias_rows != nullptr && (full_rows || row_ok))
           brow = p.bias_rows + (size_t)((m0 + row) / p.rows_per_group) * p.N + n0 + ch * OUT_COLS;
         const bool brow_vec = n0 + (ch + 1) * OUT_COLS <= p.N;     // whole chunk inside the matrix: vector loads
+        const float lo = (EXTRA && p.relu) ? 0.f : -INFINITY;
+        const uint32_t srow = smem_u32(so) + row * 128;
         if (OUT_F32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {           // 8 x 16 bytes = 32 floats
@@ -427,15 +438,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float4 b4 = bs4[j];
               o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
             }
-            if (brow) {
-              float r4[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                r4[e] = (brow_vec || n0 + ch * OUT_COLS + 4 * j + e < p.N) ? __ldg(brow + 4 * j + e) : 0.f;
-              o.x += r4[0]; o.y += r4[1]; o.z += r4[2]; o.w += r4[3];
+            if (EXTRA) {
+              if (brow && (brow_vec || n0 + ch * OUT_COLS + 4 * j < p.N)) {      // N % 8 == 0: groups are all in or out
+                const float4 r4 = __ldg(reinterpret_cast<const float4*>(brow) + j);
+                o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+              }
+              o.x = fmaxf(o.x, lo); o.y = fmaxf(o.y, lo); o.z = fmaxf(o.z, lo); o.w = fmaxf(o.w, lo);
             }
-            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            *reinterpret_cast<float4*>(srow + ((j ^ (row & 7)) << 4)) = o;
+            st_shared_v4(srow + ((j ^ (row & 7)) << 4), __float_as_uint(o.x), __float_as_uint(o.y),
+                         __float_as_uint(o.z), __float_as_uint(o.w));
           }
         } else {
 #pragma unroll
@@ -451,33 +462,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               f[2] = __fadd2_rn(f[2], make_float2(b1.x, b1.y));
               f[3] = __fadd2_rn(f[3], make_float2(b1.z, b1.w));
             }
-            if (brow) {
-              if (brow_vec) {
+            if (EXTRA) {
+              if (brow && (brow_vec || n0 + ch * OUT_COLS + 8 * j < p.N)) {      // N % 8 == 0: groups are all in or out
                 const float4 r0 = __ldg(reinterpret_cast<const float4*>(brow) + 2 * j);
                 const float4 r1 = __ldg(reinterpret_cast<const float4*>(brow) + 2 * j + 1);
                 f[0] = __fadd2_rn(f[0], make_float2(r0.x, r0.y));
                 f[1] = __fadd2_rn(f[1], make_float2(r0.z, r0.w));
                 f[2] = __fadd2_rn(f[2], make_float2(r1.x, r1.y));
                 f[3] = __fadd2_rn(f[3], make_float2(r1.z, r1.w));
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int c0 = n0 + ch * OUT_COLS + 8 * j + 2 * e;
-                  f[e].x += c0 < p.N ? __ldg(brow + 8 * j + 2 * e) : 0.f;
-                  f[e].y += c0 + 1 < p.N ? __ldg(brow + 8 * j + 2 * e + 1) : 0.f;
-                }
               }
-            }
-            if (p.relu) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) { f[e].x = fmaxf(f[e].x, 0.f); f[e].y = fmaxf(f[e].y, 0.f); }
+              for (int e = 0; e < 4; ++e) { f[e].x = fmaxf(f[e].x, lo); f[e].y = fmaxf(f[e].y, lo); }
             }
-            uint4 o;
-            o.x = pack_bf16(f[0].x, f[0].y);
-            o.y = pack_bf16(f[1].x, f[1].y);
-            o.z = pack_bf16(f[2].x, f[2].y);
-            o.w = pack_bf16(f[3].x, f[3].y);
-            *reinterpret_cast<uint4*>(srow + ((j ^ (row & 7)) << 4)) = o;
+            st_shared_v4(srow + ((j ^ (row & 7)) << 4), pack_bf16(f[0].x, f[0].y), pack_bf16(f[1].x, f[1].y),
+                         pack_bf16(f[2].x, f[2].y), pack_bf16(f[3].x, f[3].y));
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the TMA engine
@@ -489,11 +487,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (do_stats) {
           // column sums / sums of squares of the STORED bf16 values: lane = column pair, over the warp's own 32 rows
           float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+          const uint32_t so_u32 = smem_u32(so);
 #pragma unroll 8
           for (int r = 0; r < 32; ++r) {
             const int rr = q * 32 + r;
-            const uint32_t wv = *reinterpret_cast<const uint32_t*>(so + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) +
-                                                                   ((lane & 3) << 2));
+            const uint32_t wv = ld_shared_u32(so_u32 + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
             const float2 f2 = make_float2(__uint_as_float(wv << 16), __uint_as_float(wv & 0xffff0000u));
             s2 = __fadd2_rn(s2, f2);
             q2 = __ffma2_rn(f2, f2, q2);
@@ -566,11 +564,11 @@ static bool make_map(CUtensorMap* m, const void* base, bool f32, uint64_t rows, 
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int CTAS, bool OUT_F32>
+template <int BN, int CTAS, bool OUT_F32, bool EXTRA>
 static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tO, const Params& p, int sms,
                   cudaStream_t st) {
   using C = Cfg<BN, CTAS>;
-  auto kern = gemm_tc_kernel<BN, CTAS, OUT_F32>;
+  auto kern = gemm_tc_kernel<BN, CTAS, OUT_F32, EXTRA>;
   static bool configured = false;      // per instantiation
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
@@ -641,7 +639,7 @@ extern "C" int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void*
   if (lda < (a_mn_major ? M : K) || ldb < (b_mn_major ? N : K) || ldo < N) return HSP_EINVAL;
   if (stats && (out_f32 || splits != 1)) return HSP_EINVAL;
   if (splits > 1 && (!out_f32 || bias || bias_rows || relu)) return HSP_EINVAL;
-  if (bias_rows && (rows_per_group <= 0 || (N % 4) != 0 || ((uintptr_t)bias_rows % 16) != 0)) return HSP_EINVAL;
+  if (bias_rows && (rows_per_group <= 0 || (N % 8) != 0 || ((uintptr_t)bias_rows % 16) != 0)) return HSP_EINVAL;
   const int total_kb = (K + BK - 1) / BK;
   const int kb_per = (total_kb + splits - 1) / splits;
   if ((splits - 1) * kb_per >= total_kb && splits > 1) return HSP_EINVAL;
@@ -671,9 +669,13 @@ extern "C" int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void*
   p.relu = relu ? 1 : 0;
   p.debug = g_gemm_debug;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool extra = bias_rows != nullptr || relu != 0;   // the epilogue variant with the row-group bias / ReLU code
 #define HSP_GEMM_CASE(BN_, CT_)                                                          \
   if (tile_n == BN_ && ctas == CT_)                                                      \
-    return out_f32 ? launch<BN_, CT_, true>(tA, tB, tO, p, sms, st) : launch<BN_, CT_, false>(tA, tB, tO, p, sms, st)
+    return out_f32 ? (extra ? launch<BN_, CT_, true, true>(tA, tB, tO, p, sms, st)      \
+                            : launch<BN_, CT_, true, false>(tA, tB, tO, p, sms, st))    \
+                   : (extra ? launch<BN_, CT_, false, true>(tA, tB, tO, p, sms, st)     \
+                            : launch<BN_, CT_, false, false>(tA, tB, tO, p, sms, st))
   HSP_GEMM_CASE(256, 2);
   HSP_GEMM_CASE(128, 2);
   HSP_GEMM_CASE(64, 2);

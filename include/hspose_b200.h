@@ -261,7 +261,7 @@ int hsp_bn_apply_fwd(const void* x, int ldx, int M, int C, int dtype, const floa
  *   stats (optional, bf16 output): (ceil(M/128), 2, N) floats — per 128-row block the column
  *     sums and sums of squares of the values AS STORED; this is the partial layout
  *     hsp_bn_apply_fwd() consumes, so BatchNorm needs no statistics pass of its own.
- *   bias_rows (optional, (ceil(M/rows_per_group), N) floats, N % 4 == 0): a second bias shared by groups of
+ *   bias_rows (optional, (ceil(M/rows_per_group), N) floats, N % 8 == 0): a second bias shared by groups of
  *     rows_per_group consecutive rows — the per-object `f_global` block of face_head[0]
  *     (FaceRecon.py:118-121: cat[f_global repeated over the points, ...]) as a broadcast term.
  *   relu != 0: max(0, .) after the biases (the ReLU of a folded Conv1d -> BatchNorm(eval) -> ReLU block).

@@ -91,6 +91,28 @@ def test_gemm_column_slices_and_errors(cuda):
         ops.gemm_bf16(A, W[:, :512])
 
 
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,N,K,rpg,ctas", [(2056, 520, 264, 1028, 2), (1028, 1288, 328, 257, 1), (300, 64, 128, 100, 0)])
+def test_gemm_row_group_bias_and_relu(cuda, out_dtype, M, N, K, rpg, ctas):
+    """The EXTRA epilogue (its own kernel instantiation): per-row-group bias (FaceRecon.py:88-91's per-object
+    one-hot / global-feature term broadcast over the object's points) + ReLU, ragged M and N tails."""
+    import hspose_b200.ops as ops
+    A, B, bias = _mk(M, N, K, 5)
+    G = (M + rpg - 1) // rpg
+    br = torch.randn(G, N, generator=torch.Generator().manual_seed(6)).cuda()
+    ref = _ref(A, B, bias) + br.repeat_interleave(rpg, 0)[:M]
+    for relu in (False, True):
+        out = ops.gemm_bf16(A, B, bias=bias, bias_rows=br, rows_per_group=rpg, relu=relu, out_dtype=out_dtype, ctas=ctas)
+        r = ref.clamp_min(0) if relu else ref
+        tol = (2 ** -8 if out_dtype == torch.bfloat16 else 1e-4) * ref.abs().max().item()
+        assert (out.float() - r).abs().max().item() <= tol
+    if out_dtype == torch.bfloat16:      # BatchNorm partials see the biased values
+        out, st = ops.gemm_bf16(A, B, bias=bias, bias_rows=br, rows_per_group=rpg, stats=True, ctas=ctas)
+        assert torch.allclose(st[0, 0], out.float()[:128].sum(0), rtol=1e-4, atol=1e-3)
+    plain = ops.gemm_bf16(A, B, relu=True, out_dtype=out_dtype)      # ReLU alone
+    assert (plain.float() - (A.float() @ B.float().t()).clamp_min(0)).abs().max().item() <= tol
+
+
 def test_linear_bn_relu_node_matches_torch(cuda):
     """The fused Linear -> BatchNorm(train) -> ReLU autograd node (K6 + K6b) vs torch modules on the
     same bf16-rounded operands: forward, running statistics and all gradients."""
