@@ -25,6 +25,10 @@ SIGNATURES = {
     "hsp_graph_conv_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
     "hsp_graph_conv_bwd": (c_int, [P, P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P, P,
                                    P, P, c_size_t, P]),
+    "hsp_graph_conv_bwd_obj_supported": (c_int, [c_int] * 3),
+    "hsp_graph_conv_bwd_obj_workspace_bytes": (c_size_t, [c_int] * 5),
+    "hsp_graph_conv_bwd_obj": (c_int, [P, P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P,
+                                       P, P, c_size_t, P]),
     "hsp_gather_max_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "hsp_gather_max_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "hsp_orl_global_workspace_bytes": (c_size_t, [c_int] * 3),

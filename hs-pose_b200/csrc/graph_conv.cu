@@ -501,63 +501,115 @@ dir_reduce_kernel(const float* __restrict__ partial, int rows, int cols, float* 
   }
 }
 
-template <int S, typename TP>
-__global__ void __launch_bounds__(GC_THREADS)
-graph_conv_bwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
-                      const float* __restrict__ dirn, const TP* __restrict__ P,
-                      const uint8_t* __restrict__ argmax, const float* __restrict__ gout, int B,
-                      int N, int k, int C, float* __restrict__ gP, float* __restrict__ partial,
-                      int want_gbias) {
-  __shared__ int s_idx[GC_PT * GC_MAXK];
-  __shared__ float s_r[GC_PT * GC_MAXK * 3];
+// K4b, atomic variant (any S, C, N).  A point costs two dependent L2 round trips (winner byte -> support
+// value / RED); a loop over the tile's points that serialises them is latency-bound (round-1 kernel, ncu r1h:
+// issue 17 %, DRAM 19 %; running it per L2-sized chunk of objects changed nothing, tools/k4b_chunk.py).
+// Here the tile's winners and output gradients are all requested first (8 x (S + 1) independent loads per
+// thread), then the support values of HALF a tile (4 x S loads in flight), then the REDs — about five
+// round trips per tile instead of ~18.  (point, neighbour) unit direction + index come as one 16-byte
+// shared-memory broadcast as in the forward kernel.
+template <int S, typename TP, int MINB>
+__global__ void __launch_bounds__(GC_THREADS, MINB)
+graph_conv_bwd2_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
+                       const float* __restrict__ dirn, const TP* __restrict__ P,
+                       const uint8_t* __restrict__ argmax, const float* __restrict__ gout, int B,
+                       int N, int k, int C, float* __restrict__ gP, float* __restrict__ partial,
+                       int want_gbias) {
+  __shared__ float4 s_rn[GC_PT * GC_MAXK];   // (rhat.x, rhat.y, rhat.z, bits(neighbour index))
   const int c = blockIdx.z * GC_THREADS + threadIdx.x;
+  const bool live = c < C;
+  const int cc = live ? c : 0;
   const int SC = S * C, LD = (S + 1) * C;
   const int tiles = (N + GC_PT - 1) / GC_PT;
-  float dx[S], dy[S], dz[S], gx[S], gy[S], gz[S], gb[S], gbc = 0.0f;   // gb*: column sums of gP
+  constexpr int HALF = GC_PT / 2;
+  // this thread's S support directions live in shared memory (conflict-free column reads): the registers
+  // go to loads in flight
+  __shared__ float s_d[3 * S][GC_THREADS];
+  float gx[S], gy[S], gz[S], gb[S], gbc = 0.0f;   // gb*: column sums of gP
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     gx[s] = gy[s] = gz[s] = gb[s] = 0.0f;
-    dx[s] = dy[s] = dz[s] = 0.0f;
-    if (c < C) {
-      dx[s] = dirn[s * C + c];
-      dy[s] = dirn[SC + s * C + c];
-      dz[s] = dirn[2 * SC + s * C + c];
-    }
+    s_d[s][threadIdx.x] = dirn[s * C + cc];
+    s_d[S + s][threadIdx.x] = dirn[SC + s * C + cc];
+    s_d[2 * S + s][threadIdx.x] = dirn[2 * SC + s * C + cc];
   }
   for (int w = blockIdx.x; w < B * tiles; w += gridDim.x) {
     const int b = w / tiles, i0 = (w % tiles) * GC_PT;
     const int npts = min(GC_PT, N - i0);
+    const uint8_t* amb = argmax + (size_t)b * N * SC + cc;
+    const float* gob = gout + (size_t)b * N * C + cc;
+    // winners + output gradients of the first half tile: in flight while the tile is staged
+    unsigned byte[HALF][S];
+    float gv[HALF];
+    auto request = [&](int h) {
+#pragma unroll
+      for (int q = 0; q < HALF; ++q) {
+        const int row = i0 + (h + q < npts ? h + q : 0);
+        gv[q] = __ldg(gob + row * C);
+#pragma unroll
+        for (int s = 0; s < S; ++s) byte[q][s] = __ldg(amb + row * SC + s * C);
+      }
+    };
+    request(0);
+    __syncthreads();                       // previous tile's readers of s_rn are done
+    {
+      const float* xb = xyz + (size_t)b * N * 3;
+      const int32_t* ib = idx + (size_t)b * N * k;
+      for (int p = threadIdx.x; p < npts * k; p += GC_THREADS) {
+        const int i = i0 + p / k;
+        const int nb = ib[(size_t)i * k + (p % k)];
+        float r[3];
+        unit_dir(xb, i, nb, r);
+        s_rn[p] = make_float4(r[0], r[1], r[2], __int_as_float(nb));
+      }
+    }
     __syncthreads();
-    stage_tile(xyz + (size_t)b * N * 3, idx + (size_t)b * N * k, i0, npts, k, s_idx, s_r);
-    __syncthreads();
-    if (c < C) {
-      const TP* Pb = P + (size_t)b * N * LD;
-      float* gPb = gP + (size_t)b * N * LD;
-      for (int p = 0; p < npts; ++p) {
-        const size_t row = (size_t)b * N + i0 + p;
-        const float g = gout[row * C + c];
-        gPb[(size_t)(i0 + p) * LD + c] = g;  // centre term
-        gbc += g;
-        const float gs = __fdiv_rn(g, (float)S);
+    if (!live) continue;
+    const TP* Pb = P + (size_t)b * N * LD + C + c;
+    float* gPb = gP + (size_t)b * N * LD + c;
+#pragma unroll
+    for (int h = 0; h < GC_PT; h += HALF) {
+      float pv[HALF][S], g[HALF];
+      unsigned amw[HALF][2];               // winner slots packed: supports 0-3 | 4-7
+#pragma unroll
+      for (int q = 0; q < HALF; ++q) {
+        g[q] = gv[q];
+        amw[q][0] = 0u; amw[q][1] = 0u;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-          const int n = argmax[row * SC + s * C + c];
-          const float* r = s_r + 3 * (p * k + n);
-          const size_t off = (size_t)s_idx[p * k + n] * LD + C + s * C + c;
-          const float th = fmaxf(fmaf(r[2], dz[s], fmaf(r[1], dy[s], r[0] * dx[s])), 0.0f);
-          if (th > 0.0f) {
-            atomicAdd(gPb + off, gs * th);
-            gb[s] += gs * th;
-            const float gv = gs * ld_p(Pb + off);
-            gx[s] = fmaf(gv, r[0], gx[s]);
-            gy[s] = fmaf(gv, r[1], gy[s]);
-            gz[s] = fmaf(gv, r[2], gz[s]);
+          const int n = min((int)byte[q][s], k - 1);            // (clamp never taken for a forward-written byte)
+          amw[q][s >> 2] |= (unsigned)n << (8 * (s & 3));
+          const int nb = __float_as_int(s_rn[(h + q < npts ? h + q : 0) * k + n].w);   // rows past the tile: point 0's
+          pv[q][s] = ld_p(Pb + nb * LD + s * C);
+        }
+      }
+      if (h + HALF < GC_PT) request(h + HALF);                  // next half's winners: in flight under the REDs
+#pragma unroll
+      for (int q = 0; q < HALF; ++q) {
+        if (h + q < npts) {
+          gPb[(i0 + h + q) * LD] = g[q];                      // centre term
+          gbc += g[q];
+          const float gs = __fdiv_rn(g[q], (float)S);
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            const float4 rn = s_rn[(h + q) * k + ((amw[q][s >> 2] >> (8 * (s & 3))) & 0xffu)];
+            const float th = fmaxf(fmaf(rn.z, s_d[2 * S + s][threadIdx.x],
+                                        fmaf(rn.y, s_d[S + s][threadIdx.x], rn.x * s_d[s][threadIdx.x])), 0.0f);
+            if (th > 0.0f) {
+              const float contrib = gs * th;
+              atomicAdd(gPb + __float_as_int(rn.w) * LD + C + s * C, contrib);
+              gb[s] += contrib;
+              const float gvp = gs * pv[q][s];
+              gx[s] = fmaf(gvp, rn.x, gx[s]);
+              gy[s] = fmaf(gvp, rn.y, gy[s]);
+              gz[s] = fmaf(gvp, rn.z, gz[s]);
+            }
           }
         }
       }
     }
   }
-  if (c < C) {
+  if (live) {
     const int pcols = want_gbias ? 3 * SC + (S + 1) * C : 3 * SC;
     float* pr = partial + (size_t)blockIdx.x * pcols;
 #pragma unroll
@@ -572,6 +624,185 @@ graph_conv_bwd_kernel(const float* __restrict__ xyz, const int32_t* __restrict__
       for (int s = 0; s < S; ++s) pr[3 * SC + C + s * C + c] = gb[s];
     }
   }
+}
+
+// K4b v3 ("object-resident").  ncu of v2 on the 128-channel layer: the L1 -> crossbar request path is 83 %
+// busy — every (point, support, channel) winner is its own 4-byte RED / 2-byte load to one of ~15 different
+// rows per warp instruction (57 M RED requests, 102 M sectors for 118 M elements), and gP costs a 539 MB
+// memset + a 539 MB -> 269 MB cast pass on top.  Here one CTA owns the gradient slab of (object b, support s,
+// 32 channels): N x 32 floats in shared memory (131.6 KB at N = 1028), lane = channel, so the scattered adds
+// are shared-memory atomics with bank = lane (conflict-free across rows), and the slab leaves the SM ONCE, as
+// whole 64-byte (bf16) / 128-byte (fp32) row segments in the caller's dtype — no memset, no global RED, no
+// cast pass.  Item s == S writes the centre columns.  Each warp walks batches of 8 points: winners and
+// output gradients first, then the 8 support values (independent loads in flight), then the adds.
+// gdirn / gbias: per-thread sums over the warp's points, fixed-order sum over the 8 warps, one partial row
+// per object, fixed-order column reduction (dir_reduce_kernel) — deterministic as before.
+
+__device__ __forceinline__ void st_g(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_g(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <int S, typename TP, typename TO, int THREADS, int GO_PB>
+__global__ void __launch_bounds__(THREADS)
+graph_conv_bwd_obj_kernel(const float4* __restrict__ rnbuf, const float* __restrict__ dirn,
+                          const TP* __restrict__ P, const uint8_t* __restrict__ argmax,
+                          const float* __restrict__ gout, const float* __restrict__ gmax, int N, int k, int C,
+                          TO* __restrict__ gP, float* __restrict__ partial, int want_gbias) {
+  constexpr int WARPS = THREADS / 32;
+  extern __shared__ __align__(16) unsigned char go_smem[];
+  float* acc = reinterpret_cast<float*>(go_smem);                          // [N][32]
+  float* s_red = acc + (size_t)N * 32;                                     // [4][WARPS][32]
+  const int b = blockIdx.z, s = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int SC = S * C, LD = (S + 1) * C;
+  const int pcols = want_gbias ? 3 * SC + (S + 1) * C : 3 * SC;
+  const float* gob = gout + (size_t)b * N * C + c;
+  TO* gPb = gP + (size_t)b * N * LD;
+  float* prow = partial + (size_t)b * pcols;
+  if (s == S) {                              // centre term: gP[:, :C] = gout, gbias[:C] = its column sums
+    float gbc = 0.0f;
+#pragma unroll 8
+    for (int j = warp; j < N; j += WARPS) {
+      const float g = __ldg(gob + (size_t)j * C);
+      st_g(gPb + (size_t)j * LD + c, g);
+      gbc += g;
+    }
+    if (want_gbias) {
+      s_red[warp * 32 + lane] = gbc;
+      __syncthreads();
+      if (warp == 0) {
+        float t = 0.0f;
+#pragma unroll 8
+        for (int w = 0; w < WARPS; ++w) t += s_red[w * 32 + lane];
+        prow[3 * SC + c] = t;
+      }
+    }
+    return;
+  }
+  for (int e = threadIdx.x; e < N * 32; e += THREADS) acc[e] = 0.0f;    // (+0.0f and integer 0 share the bit pattern)
+  // bf16 output: the slab accumulates in 32-bit FIXED POINT — shared-memory integer adds are one native
+  // instruction (a float add is a compare-and-swap loop) and associative, so gP is bit-reproducible.  Scale:
+  // |contribution| <= max|gout| / S over the CTA's rows x channels, at most N contributions per accumulator,
+  // so 1.5e9 / (N * max|gout| / S) cannot overflow; the quantum is <= 2^-20 of that maximum (bf16 rounds at 2^-9).
+  constexpr bool FIXED = sizeof(TO) == 2;
+  float scale = 1.0f;
+  if (FIXED) {                               // max|gout| over the CTA's rows x channels (absmax_slab_kernel)
+    const float m = __ldg(gmax + (size_t)b * gridDim.x + blockIdx.x);
+    scale = m > 0.0f ? 1.5e9f * (float)S / ((float)N * m) : 1.0f;
+  }
+  const float inv_scale = __fdiv_rn(1.0f, scale);
+  const float dx = dirn[s * C + c], dy = dirn[SC + s * C + c], dz = dirn[2 * SC + s * C + c];
+  const uint8_t* amb = argmax + (size_t)b * N * SC + s * C + c;
+  const TP* Pb = P + (size_t)b * N * LD + C + s * C + c;
+  const float4* rnb = rnbuf + (size_t)b * N * k;        // (rhat, neighbour index) of every (point, slot) pair
+  float gx = 0.0f, gy = 0.0f, gz = 0.0f, gb = 0.0f;
+  unsigned win[GO_PB];
+  float g8[GO_PB];
+  auto request = [&](int base) {             // winners + output gradients of a batch (rows clamped into the object)
+#pragma unroll
+    for (int p = 0; p < GO_PB; ++p) {
+      const int row = min(base + p, N - 1);
+      win[p] = __ldg(amb + (size_t)row * SC);
+      g8[p] = __ldg(gob + (size_t)row * C);
+    }
+  };
+  request(warp * GO_PB);
+  __syncthreads();
+  for (int base = warp * GO_PB; base < N; base += WARPS * GO_PB) {
+    const int npts = min(GO_PB, N - base);
+    float4 rn[GO_PB];
+    float pv[GO_PB], gs[GO_PB];
+#pragma unroll
+    for (int p = 0; p < GO_PB; ++p) {        // a warp's lanes read inside one point's k x 16-byte row
+      const int n = min((int)win[p], k - 1);                     // (clamp never taken for a forward-written byte)
+      rn[p] = __ldg(rnb + (size_t)min(base + p, N - 1) * k + n);
+      gs[p] = __fdiv_rn(g8[p], (float)S);
+    }
+    if (base + WARPS * GO_PB < N) request(base + WARPS * GO_PB);   // next batch: in flight under this one
+#pragma unroll
+    for (int p = 0; p < GO_PB; ++p) pv[p] = ld_p(Pb + (size_t)__float_as_int(rn[p].w) * LD);
+#pragma unroll
+    for (int p = 0; p < GO_PB; ++p) {
+      if (p < npts) {
+        const float th = fmaxf(fmaf(rn[p].z, dz, fmaf(rn[p].y, dy, rn[p].x * dx)), 0.0f);
+        if (th > 0.0f) {
+          const float contrib = gs[p] * th;
+          if (FIXED) atomicAdd(reinterpret_cast<int*>(acc) + __float_as_int(rn[p].w) * 32 + lane, __float2int_rn(contrib * scale));
+          else atomicAdd(acc + __float_as_int(rn[p].w) * 32 + lane, contrib);
+          gb += contrib;
+          const float gvp = gs[p] * pv[p];
+          gx = fmaf(gvp, rn[p].x, gx);
+          gy = fmaf(gvp, rn[p].y, gy);
+          gz = fmaf(gvp, rn[p].z, gz);
+        }
+      }
+    }
+  }
+  __syncthreads();                           // slab complete
+  s_red[(0 * WARPS + warp) * 32 + lane] = gx;
+  s_red[(1 * WARPS + warp) * 32 + lane] = gy;
+  s_red[(2 * WARPS + warp) * 32 + lane] = gz;
+  s_red[(3 * WARPS + warp) * 32 + lane] = gb;
+  // the slab leaves as whole row segments: two rows per warp instruction (half-warp = 16 channel pairs)
+  {
+    const int hl = lane & 15, hr = lane >> 4;
+    for (int j = warp * 2 + hr; j < N; j += WARPS * 2) {
+      const float2 v = *reinterpret_cast<const float2*>(acc + j * 32 + 2 * hl);
+      TO* dst = gPb + (size_t)j * LD + C + s * C + blockIdx.x * 32 + 2 * hl;
+      if (FIXED) {
+        *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(
+            (float)__float_as_int(v.x) * inv_scale, (float)__float_as_int(v.y) * inv_scale);
+      } else {
+        *reinterpret_cast<float2*>(dst) = v;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp < 4 && (warp < 3 || want_gbias)) {
+    float t = 0.0f;
+#pragma unroll 8
+    for (int w = 0; w < WARPS; ++w) t += s_red[(warp * WARPS + w) * 32 + lane];
+    if (warp < 3) prow[warp * SC + s * C + c] = t;
+    else prow[3 * SC + C + s * C + c] = t;
+  }
+}
+
+// max |gout[b, :, 32 cg .. 32 cg + 31]| for the fixed-point scale of the bf16 slabs: grid (C / 32, B)
+__global__ void __launch_bounds__(256)
+absmax_slab_kernel(const float* __restrict__ gout, int N, int C, float* __restrict__ out) {
+  __shared__ float sh[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* g = gout + (size_t)blockIdx.y * N * C + blockIdx.x * 32 + lane;
+  float m = 0.0f;
+#pragma unroll 8
+  for (int j = warp; j < N; j += 8) m = fmaxf(m, fabsf(__ldg(g + (size_t)j * C)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) sh[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, sh[w]);
+    out[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = m;
+  }
+}
+
+// (unit direction, neighbour index) of every (point, neighbour slot) pair, once per layer call
+__global__ void __launch_bounds__(256)
+pair_dirs_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx, int N, int k, int total,
+                 float4* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int bi = t / k, b = bi / N, i = bi % N;
+  const int j = idx[t];
+  float r[3];
+  unit_dir(xyz + (size_t)b * N * 3, i, j, r);
+  out[t] = make_float4(r[0], r[1], r[2], __int_as_float(j));
+}
+
+static int bwd_obj_threads(int N) { return N >= 512 ? 1024 : 256; }
+static size_t bwd_obj_smem(int N, int k) {
+  (void)k;
+  return (size_t)N * 32 * sizeof(float) + (size_t)4 * (bwd_obj_threads(N) / 32) * 32 * sizeof(float);
 }
 
 static int bwd_ctas(int B, int N) {
@@ -715,11 +946,11 @@ extern "C" int hsp_graph_conv_bwd(const float* xyz, const int32_t* idx, const fl
   const int ctas = bwd_ctas(B, N);
   dim3 grid(ctas, 1, (C + GC_THREADS - 1) / GC_THREADS);
   if (p_dtype == HSP_DTYPE_BF16) {
-    HSP_DISPATCH_S(S, (graph_conv_bwd_kernel<S, __nv_bfloat16><<<grid, GC_THREADS, 0, st>>>(
+    HSP_DISPATCH_S(S, (graph_conv_bwd2_kernel<S, __nv_bfloat16, 4><<<grid, GC_THREADS, 0, st>>>(
                           xyz, idx, dirn, (const __nv_bfloat16*)P, argmax, gout, B, N, k, C, gP,
                           (float*)workspace, want_gbias)));
   } else if (p_dtype == HSP_DTYPE_F32) {
-    HSP_DISPATCH_S(S, (graph_conv_bwd_kernel<S, float><<<grid, GC_THREADS, 0, st>>>(
+    HSP_DISPATCH_S(S, (graph_conv_bwd2_kernel<S, float, 4><<<grid, GC_THREADS, 0, st>>>(
                           xyz, idx, dirn, (const float*)P, argmax, gout, B, N, k, C, gP,
                           (float*)workspace, want_gbias)));
   } else {
@@ -729,6 +960,76 @@ extern "C" int hsp_graph_conv_bwd(const float* xyz, const int32_t* idx, const fl
   const int cols_a = 3 * S * C, cols = want_gbias ? cols_a + (S + 1) * C : cols_a;
   dir_reduce_kernel<<<(cols + 31) / 32, dim3(32, 8), 0, st>>>((const float*)workspace, ctas, cols, gdirn,
                                                           cols_a, gbias);
+  HSP_LAUNCH_CHECK();
+  return HSP_OK;
+}
+
+// Object-resident variant (graph_conv_bwd_obj_kernel): gP is written once, in `gp_dtype`, with no memset.
+// Supported when C % 32 == 0 and the N x 32 fp32 slab + staging fit in shared memory (N <= ~1600).
+extern "C" int hsp_graph_conv_bwd_obj_supported(int N, int k, int C) {
+  using namespace hsp;
+  return N > 0 && k > 0 && k <= GC_MAXK && C > 0 && (C % 32) == 0 && bwd_obj_smem(N, k) <= 220 * 1024 ? 1 : 0;
+}
+extern "C" size_t hsp_graph_conv_bwd_obj_workspace_bytes(int B, int N, int k, int S, int C) {
+  using namespace hsp;
+  if (bad_dims(B, N, k, S, C) || B == 0) return 0;
+  return (size_t)B * (3 * S + S + 1) * C * sizeof(float) + (size_t)B * N * k * sizeof(float4) + 16 +
+         (size_t)B * (C / 32 + 1) * sizeof(float);
+}
+extern "C" int hsp_graph_conv_bwd_obj(const float* xyz, const int32_t* idx, const float* dirn, const void* P,
+                                      int p_dtype, const uint8_t* argmax, const float* gout, int B, int N,
+                                      int k, int S, int C, void* gP, int gp_dtype, float* gdirn, float* gbias,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace hsp;
+  if (!xyz || !idx || !dirn || !P || !argmax || !gout || !gP || !gdirn || bad_dims(B, N, k, S, C))
+    return HSP_EINVAL;
+  if (!hsp_graph_conv_bwd_obj_supported(N, k, C) || S != 7) return HSP_EINVAL;
+  if ((p_dtype != HSP_DTYPE_F32 && p_dtype != HSP_DTYPE_BF16) || (gp_dtype != HSP_DTYPE_F32 && gp_dtype != HSP_DTYPE_BF16))
+    return HSP_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) {
+    if (gbias && cudaMemsetAsync(gbias, 0, sizeof(float) * (S + 1) * C, st) != cudaSuccess) return HSP_ELAUNCH;
+    return cudaMemsetAsync(gdirn, 0, sizeof(float) * 3 * S * C, st) == cudaSuccess ? HSP_OK : HSP_ELAUNCH;
+  }
+  if (!workspace || workspace_bytes < hsp_graph_conv_bwd_obj_workspace_bytes(B, N, k, S, C)) return HSP_EWORKSPACE;
+  const int want_gbias = gbias != nullptr;
+  const size_t smem = bwd_obj_smem(N, k);
+  dim3 grid(C / 32, S + 1, B);
+  if ((long)B * N * k > 0x7fffffffL) return HSP_EINVAL;
+  float* partial = (float*)workspace;
+  float4* rnbuf = (float4*)(((uintptr_t)(partial + (size_t)B * (3 * S + S + 1) * C) + 15) & ~(uintptr_t)15);
+  const int total = B * N * k;
+  pair_dirs_kernel<<<(total + 255) / 256, 256, 0, st>>>(xyz, idx, N, k, total, rnbuf);
+  HSP_LAUNCH_CHECK();
+  float* gmax = (float*)(rnbuf + total);
+  if (gp_dtype == HSP_DTYPE_BF16) {
+    absmax_slab_kernel<<<dim3(C / 32, B), 256, 0, st>>>(gout, N, C, gmax);
+    HSP_LAUNCH_CHECK();
+  }
+#define HSP_GCO_T(TP_, TO_, T_, PB_)                                                                             \
+  do {                                                                                                           \
+    auto kern = graph_conv_bwd_obj_kernel<7, TP_, TO_, T_, PB_>;                                                 \
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)      \
+      return HSP_ELAUNCH;                                                                                        \
+    kern<<<grid, T_, smem, st>>>(rnbuf, dirn, (const TP_*)P, argmax, gout, gmax, N, k, C, (TO_*)gP, partial,     \
+                                 want_gbias);                                                                    \
+  } while (0)
+#define HSP_GCO(TP_, TO_)                                                                                        \
+  do {                                                                                                           \
+    if (threads == 1024) HSP_GCO_T(TP_, TO_, 1024, 4);                                                           \
+    else HSP_GCO_T(TP_, TO_, 256, 4);                                                                            \
+  } while (0)
+  const int threads = bwd_obj_threads(N);
+  if (p_dtype == HSP_DTYPE_BF16) {
+    if (gp_dtype == HSP_DTYPE_BF16) HSP_GCO(__nv_bfloat16, __nv_bfloat16); else HSP_GCO(__nv_bfloat16, float);
+  } else {
+    if (gp_dtype == HSP_DTYPE_BF16) HSP_GCO(float, __nv_bfloat16); else HSP_GCO(float, float);
+  }
+#undef HSP_GCO_T
+#undef HSP_GCO
+  HSP_LAUNCH_CHECK();
+  const int cols_a = 3 * S * C, cols = want_gbias ? cols_a + (S + 1) * C : cols_a;
+  dir_reduce_kernel<<<(cols + 31) / 32, dim3(32, 8), 0, st>>>(partial, B, cols, gdirn, cols_a, gbias);
   HSP_LAUNCH_CHECK();
   return HSP_OK;
 }

@@ -191,17 +191,29 @@ def _graph_conv_fwd_raw(xyz, idx32, dirn, P, S, C, want_argmax):
     return out, am
 
 
-def _graph_conv_bwd_raw(xyz, idx32, dirn, P, am, gout, S, C, want_gbias=False):
+def _graph_conv_bwd_raw(xyz, idx32, dirn, P, am, gout, S, C, want_gbias=False, gp_dtype=torch.float32, variant="auto"):
+    """K4b.  variant "obj" (object-resident slabs, gP written once in gp_dtype) when the shape allows it,
+    else "atomic" (fp32 gP via global float atomics; a bf16 gP is then one cast pass)."""
     B, N, k = idx32.shape
     dt = BF16 if P.dtype == torch.bfloat16 else F32
     with torch.cuda.device(xyz.device):
         lib = _lib.load()
-        ws = _workspace(lib.hsp_graph_conv_bwd_workspace_bytes(B, N, k, S, C), xyz.device)
-        gP = torch.empty(B, N, (S + 1) * C, dtype=torch.float32, device=xyz.device)
         gdirn = torch.empty_like(dirn)
         gbias = torch.empty((S + 1) * C, dtype=torch.float32, device=xyz.device) if want_gbias else None
-        _call("hsp_graph_conv_bwd", _p(xyz), _p(idx32), _p(dirn), _p(P), dt, _p(am), _p(gout),
-              B, N, k, S, C, _p(gP), _p(gdirn), _p(gbias), _p(ws), ws.numel(), _stream())
+        use_obj = S == 7 and lib.hsp_graph_conv_bwd_obj_supported(N, k, C) == 1 if variant == "auto" else variant == "obj"
+        if use_obj:
+            ws = _workspace(lib.hsp_graph_conv_bwd_obj_workspace_bytes(B, N, k, S, C), xyz.device)
+            gP = torch.empty(B, N, (S + 1) * C, dtype=gp_dtype, device=xyz.device)
+            _call("hsp_graph_conv_bwd_obj", _p(xyz), _p(idx32), _p(dirn), _p(P), dt, _p(am), _p(gout), B, N, k, S, C,
+                  _p(gP), BF16 if gp_dtype == torch.bfloat16 else F32, _p(gdirn), _p(gbias), _p(ws), ws.numel(),
+                  _stream())
+        else:
+            ws = _workspace(lib.hsp_graph_conv_bwd_workspace_bytes(B, N, k, S, C), xyz.device)
+            gP = torch.empty(B, N, (S + 1) * C, dtype=torch.float32, device=xyz.device)
+            _call("hsp_graph_conv_bwd", _p(xyz), _p(idx32), _p(dirn), _p(P), dt, _p(am), _p(gout),
+                  B, N, k, S, C, _p(gP), _p(gdirn), _p(gbias), _p(ws), ws.numel(), _stream())
+            if gp_dtype != torch.float32:
+                gP = gP.to(gp_dtype)
     return (gP, gdirn, gbias) if want_gbias else (gP, gdirn)
 
 
@@ -266,9 +278,10 @@ class _HSConvMixed(torch.autograd.Function):
         B, N = idx32.shape[0], idx32.shape[1]
         Cin = fm16.shape[1]
         gout = _need(gout.float(), torch.float32, "gout")
-        gP, gdirn, gb = _graph_conv_bwd_raw(xyz, idx32, dirn, P, am, gout, S, C, want_gbias=True)
-        # weight / input gradients on the K6 kernel (bf16 operands, fp32 accumulate): one cast pass over gP
-        gP16 = gP.view(B * N, (S + 1) * C).to(torch.bfloat16)
+        # weight / input gradients on the K6 kernel (bf16 operands, fp32 accumulate): K4b emits gP in bf16
+        gP16, gdirn, gb = _graph_conv_bwd_raw(xyz, idx32, dirn, P, am, gout, S, C, want_gbias=True,
+                                              gp_dtype=torch.bfloat16)
+        gP16 = gP16.view(B * N, (S + 1) * C)
         gfm = gemm_bf16(gP16, W16).view(B, N, Cin).float() if ctx.needs_input_grad[3] else None
         gW = gemm_bf16(fm16, gP16, a_mn=True, b_mn=True, out_dtype=torch.float32,
                        splits=gemm_splits(Cin, (S + 1) * C, B * N))

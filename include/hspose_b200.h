@@ -122,6 +122,18 @@ int hsp_graph_conv_bwd(const float* xyz, const int32_t* idx, const float* dirn,
                        int B, int N, int k, int S, int C, float* gP, float* gdirn,
                        float* gbias, void* workspace, size_t workspace_bytes, void* stream);
 
+/* K4b, object-resident variant: one CTA owns the gradient slab of (object, support, 32 channels) in shared memory, so
+ * gP is written exactly once, in `gp_dtype` (HSP_DTYPE_F32 / HSP_DTYPE_BF16), without a memset, global float atomics or
+ * a cast pass; gdirn / gbias as hsp_graph_conv_bwd (bit-reproducible).  Same reference semantics (gcn3d.py:158-181
+ * backward through index_put_(accumulate=True), gcn3d.py:39-47).  Requires S == 7, C % 32 == 0 and a slab that fits
+ * shared memory: ask hsp_graph_conv_bwd_obj_supported first (HSP_EINVAL otherwise).  Workspace: the _obj_ query. */
+int hsp_graph_conv_bwd_obj_supported(int N, int k, int C);
+size_t hsp_graph_conv_bwd_obj_workspace_bytes(int B, int N, int k, int S, int C);
+int hsp_graph_conv_bwd_obj(const float* xyz, const int32_t* idx, const float* dirn, const void* P, int p_dtype,
+                           const uint8_t* argmax, const float* gout, int B, int N, int k, int S, int C, void* gP,
+                           int gp_dtype, float* gdirn, float* gbias, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
 /* ------------------------------------------------------------------ K5 ---
  * Row gather + max over neighbours, evaluated at selected rows only:
  *   out[b,r,c] = max_{n<kuse} feat[b, idx[b, rows[r], n], c]

@@ -212,6 +212,60 @@ def test_gather_ops_golden(cuda, golden):
     assert np.array_equal(up.cpu().numpy(), g["up_out"])
 
 
+@pytest.mark.parametrize("B,N,k,C,pdt", [(3, 1028, 20, 128, torch.bfloat16), (2, 257, 20, 256, torch.float32),
+                                          (5, 64, 8, 512, torch.bfloat16), (2, 100, 7, 32, torch.float32)])
+def test_graph_conv_bwd_object_resident_vs_atomic(cuda, B, N, k, C, pdt):
+    """K4b, both kernels (hsp_graph_conv_bwd: global float atomics; hsp_graph_conv_bwd_obj: shared-memory slabs) give
+    the gradients of gcn3d.py:158-181 — the atomic one is pinned to autograd of the oracle above.  fp32 gP: equal up
+    to the order of the additions; bf16 gP (fixed-point slab): within one bf16 rounding, and bit-reproducible."""
+    ops = _ops()
+    S = 7
+    g = torch.Generator().manual_seed(B * N + C)
+    xyz = (torch.randn(B, N, 3, generator=g) * 0.05).to(cuda)
+    idx = ops.knn3(xyz, xyz, k)[1]
+    dirn = torch.nn.functional.normalize(torch.randn(3, S * C, generator=g), dim=0).to(cuda)
+    P = torch.randn(B, N, (S + 1) * C, generator=g).to(cuda).to(pdt)
+    _, am = ops._graph_conv_fwd_raw(xyz, idx, dirn, P, S, C, True)
+    gout = (torch.randn(B, N, C, generator=g) * torch.rand(1, 1, C, generator=g) * 3).to(cuda)
+    ref = ops._graph_conv_bwd_raw(xyz, idx, dirn, P, am, gout, S, C, want_gbias=True, variant="atomic")
+    got = ops._graph_conv_bwd_raw(xyz, idx, dirn, P, am, gout, S, C, want_gbias=True, variant="obj")
+    for a, b in zip(got, ref):
+        assert a.dtype == torch.float32 and (a - b).abs().max().item() <= 2e-6 * b.abs().max().item()
+    got16 = ops._graph_conv_bwd_raw(xyz, idx, dirn, P, am, gout, S, C, want_gbias=True, variant="obj",
+                                    gp_dtype=torch.bfloat16)
+    assert got16[0].dtype == torch.bfloat16
+    # bf16 rounding (2^-9 relative) + the fixed-point quantum (<= 2^-20 of the slab's largest possible sum)
+    err = (got16[0].float() - ref[0]).abs()
+    assert bool((err <= 2 ** -8 * ref[0].abs() + 1e-5 * ref[0].abs().max()).all())
+    again = ops._graph_conv_bwd_raw(xyz, idx, dirn, P, am, gout, S, C, want_gbias=True, variant="obj",
+                                    gp_dtype=torch.bfloat16)
+    assert all(torch.equal(a, b) for a, b in zip(got16, again))           # bit-reproducible, all three outputs
+    no_bias = ops._graph_conv_bwd_raw(xyz, idx, dirn, P, am, gout, S, C, variant="obj")
+    assert torch.equal(no_bias[1], got[1])
+    # zero upstream gradient: the scale guard
+    z = ops._graph_conv_bwd_raw(xyz, idx, dirn, P, am, torch.zeros_like(gout), S, C, variant="obj", gp_dtype=torch.bfloat16)
+    assert float(z[0].abs().max()) == 0.0 and float(z[1].abs().max()) == 0.0
+
+
+def test_graph_conv_bwd_object_resident_limits(cuda):
+    from hspose_b200 import _lib
+    lib = _lib.load()
+    assert lib.hsp_graph_conv_bwd_obj_supported(1028, 20, 128) == 1
+    assert lib.hsp_graph_conv_bwd_obj_supported(1028, 20, 100) == 0        # C % 32
+    assert lib.hsp_graph_conv_bwd_obj_supported(4096, 20, 128) == 0        # slab larger than shared memory
+    ops = _ops()
+    # unsupported shapes take the atomic kernel (and a cast pass for a bf16 gP)
+    g = torch.Generator().manual_seed(1)
+    xyz = (torch.randn(1, 2100, 3, generator=g) * 0.05).to(cuda)
+    idx = ops.knn3(xyz, xyz, 8)[1]
+    dirn = torch.nn.functional.normalize(torch.randn(3, 7 * 32, generator=g), dim=0).to(cuda)
+    P = torch.randn(1, 2100, 8 * 32, generator=g).to(cuda)
+    _, am = ops._graph_conv_fwd_raw(xyz, idx, dirn, P, 7, 32, True)
+    gout = torch.randn(1, 2100, 32, generator=g).to(cuda)
+    a = ops._graph_conv_bwd_raw(xyz, idx, dirn, P, am, gout, 7, 32, gp_dtype=torch.bfloat16)
+    assert a[0].dtype == torch.bfloat16 and a[0].shape == (1, 2100, 256)
+
+
 def test_gather_ops_backward_vs_autograd(cuda):
     ops = _ops()
     g = torch.Generator().manual_seed(3)

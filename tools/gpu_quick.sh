@@ -1,13 +1,12 @@
 #!/bin/bash
-# Short GPU visit: GEMM tests, the output-bound GEMM shapes, one bench line and the launch list of two steps.
+# Short GPU visit: selected tests, one bench line and the launch list of two steps.
 mkdir -p gpurun_out
 TAG=${1:-q}
-(timeout 600 python -m pytest tests/test_gemm_gpu.py -m gpu -q 2>&1 | tail -4)
-DBG=0 CTAS=2 TILES=256 timeout 200 python tools/gemm_sweep.py p 2>&1 | tail -4
-DBG=0 CTAS=2 TILES=256 timeout 200 python tools/gemm_sweep.py fwd 2>&1 | tail -3
+SEL=${2:-tests/test_kernels_gpu.py}
+(timeout 900 python -m pytest $SEL -m gpu -q -x 2>&1 | grep -v "UserWarning\|run_backward" | tail -8)
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 head -c 300 gpurun_out/bench_$TAG.json; echo
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
    --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_$TAG.log 2>&1
 python tools/summarize_launches.py gpurun_out/launches_$TAG.csv 2 > gpurun_out/${TAG}_launches_summary.txt 2>/dev/null
-head -30 gpurun_out/${TAG}_launches_summary.txt
+head -34 gpurun_out/${TAG}_launches_summary.txt
