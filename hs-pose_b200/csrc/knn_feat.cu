@@ -289,7 +289,7 @@ extern "C" int hsp_knn_feat(const float* feat, int B, int N, int D, int k, int d
   if (B == 0) return HSP_OK;
   if (!workspace || workspace_bytes < hsp_knn_feat_workspace_bytes(B, N)) return HSP_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  // D = 128 (any N) and D = 256 (N <= 512): tensor-core filter (tcgen05 + TMEM) + exact FP32 refine, bit-identical results
+  // D = 128 / 256, N >= 128: tensor-core filter (tcgen05 + TMEM) + exact FP32 refine, bit-identical results
   // (knn_feat_tc.cu).  HSP_KNN_FEAT_EXACT=1 forces the all-FP32 kernel below (A/B testing).
   static const bool force_exact = getenv("HSP_KNN_FEAT_EXACT") != nullptr;
   if (knn_feat_tc_supported(N, D, K) && !force_exact && (((uintptr_t)feat) & 15) == 0)

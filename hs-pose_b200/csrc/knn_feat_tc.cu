@@ -1,4 +1,4 @@
-// K2-TC — feature-space KNN (D = 128; D = 256 for N <= 512) as "tensor-core filter + exact refine".
+// K2-TC — feature-space KNN (D = 128 or 256) as "tensor-core filter + exact refine".
 //
 // Replaces get_neighbor_index(feature_map, k) (reference gcn3d.py:15-24, RF-F mode of
 // get_receptive_fields gcn3d.py:189-209) for D = 128 with results BIT-IDENTICAL to the exact
@@ -7,14 +7,15 @@
 //  1. kf_split / kf_norm (pre-pass): every feature row is split into bf16 hi + bf16 lo
 //     (x ~ hi + lo, |residual| <= 2^-18 |x|) and written in UMMA "core-matrix" order
 //     ([64-row tile][16-byte k-chunk][row][8 bf16]); |f|^2 is the exact sequential FP32 sum.
-//  2. knn_feat_tc_kernel: one CTA = 128 query rows of one object.  The query block (hi, lo) and
-//     64-candidate sub-tiles are brought into shared memory by TMA bulk copies
-//     (cp.async.bulk + mbarrier complete_tx) and multiplied on the 5th-gen tensor cores
-//     (tcgen05.mma kind::f16, M=128 N=64 K=16; hi*hi + hi*lo + lo*hi, FP32 accumulate in TMEM):
-//     up to 512 approximate inner products per row stay resident in TMEM.
-//  3. Epilogue (thread = TMEM lane = query row): approximate distances d~ = q_j - 2*inner~.
-//     32 running "slot minima" give an upper bound tau on the K-th smallest d~; every candidate
-//     with d~ <= tau + 2*eps survives (eps bounds |d~ - d_fp32| from the row norms), ~K+10 of 1028.
+//  2. knn_feat_tc2_kernel: one CTA = 128 query rows of one object, warp-specialised (TMA / MMA / 4 epilogue warps).
+//     The query block (hi, lo) and 64-candidate sub-tiles arrive in shared memory by TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx) and are multiplied on the 5th-gen tensor cores
+//     (tcgen05.mma kind::f16, M=128 N=64 K=16; hi*hi + lo*hi + hi*lo, FP32 accumulate) into a ring of four
+//     64-column TMEM slots.
+//  3. Epilogue (thread = TMEM lane = query row): approximate distances d~ = q_j - 2*inner~.  Sweep 1 folds every
+//     candidate into 64 running "slot minima"; the K-th smallest of them is an upper bound tau on the K-th smallest
+//     d~.  Sweep 2 (the inner products are recomputed) keeps every candidate with d~ <= tau + 2*eps (eps bounds
+//     |d~ - d_fp32| from the row norms), ~K+6 of 1028.
 //  4. Refine: for the survivors only, the EXACT sequential-FMA FP32 distance (same expression
 //     and order as knn_feat.cu / oracle) is evaluated and the exact (distance, index) top-K is
 //     taken.  If eps is a valid bound the survivors contain the exact top-K, so the result does
@@ -32,11 +33,9 @@ constexpr int DK = 128;                     // features per MMA pass (a "d-half"
 constexpr int KC = DK / 8;                  // 16-byte k-chunks per row
 constexpr int TILE_BYTES = KC * TR * 16;    // one (tile, hi|lo) block: 16 KB
 constexpr int QROWS = 128;                  // query rows per CTA = UMMA M
-constexpr int ROUND_COLS = 512;             // TMEM columns = candidates resident per round
 constexpr int LCAP = 92;                    // survivor list capacity per row (shared memory, 8 B entries)
 constexpr int SLOTS = 64;                   // running slot minima per row (slot = column mod 64)
 constexpr int SPITCH = DK + 4;              // staged candidate row pitch (floats): conflict-free LDS.128
-constexpr int THREADS = 128;
 // |d~ - d_fp32| <= EPS_REL * |f_i| * |f_j|.  Budget (units of |f_i||f_j|, x2 for the -2*inner factor):
 // dropped lo*lo and residual terms of the bf16 split 3 * 2^-18 = 1.1e-5; FP32 accumulator rounding of the
 // 24 MMA updates (16 exact bf16 products each) 24 * 2^-23 = 2.9e-6; the exact kernel's own sequential
@@ -55,6 +54,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -224,210 +226,211 @@ __device__ __forceinline__ void sort_regs(float (&m)[NS]) {
   }
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
-knn_feat_tc_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* __restrict__ glo,
-                   const float* __restrict__ qn, const float* __restrict__ qmax, int N, int T64, int K, int nd,
-                   float eps_rel, uint2* __restrict__ surv, int* __restrict__ surv_cnt) {
+// ---------------------------------------------------------------------------------------------------
+// The filter kernel: warp-specialised, two sweeps, two CTAs per SM.
+//
+// The round-1 kernel kept MMA and epilogue strictly serial inside a 4-warp CTA that owned all 512 TMEM columns
+// (ncu r1f: tensor pipe 14 %, issue 20 %, warps active 6 %) and re-derived its threshold every 512 columns
+// (three 64-key register sorts per row, survivors of early rounds re-filtered); A/B in profiles/r2_k2_ab.md.  Here
+//   * warp 4 = TMA producer (16 KB hi / lo candidate tiles through a 2-stage ring), warp 5 = MMA issuer,
+//     warps 0-3 = epilogue (thread = TMEM lane = query row); the accumulator is a ring of four 64-column
+//     TMEM slots, so the tensor cores run up to four candidate sub-tiles ahead of the epilogue;
+//   * 256 TMEM columns and 97 KB of shared memory per CTA (D = 128): TWO CTAs per SM;
+//   * the inner products are computed TWICE (the tensor pipe has the room): sweep 1 only folds them into the 64
+//     running slot minima; ONE register sort gives tau = K-th smallest slot minimum over ALL candidates; sweep 2
+//     collects d~ <= tau + 2 eps straight into the global survivor list — the tightest threshold from the start
+//     (~K + 6 survivors instead of ~35, no re-filtering, a third less work for the refine);
+//   * D = 256 keeps both d-halves of the query block resident (160 KB, one CTA per SM) and accumulates them in
+//     the slot, so N is no longer limited to one TMEM round.
+// The filter's contract is unchanged (survivors contain the exact top-K whenever eps bounds |d~ - d_fp32|).
+constexpr int THREADS2 = 192;
+constexpr int NSLOT = 4;                    // 64-column TMEM accumulator slots
+
+template <int ND>
+__global__ void __launch_bounds__(THREADS2, ND == 1 ? 2 : 1)
+knn_feat_tc2_kernel(const __nv_bfloat16* __restrict__ ghi, const __nv_bfloat16* __restrict__ glo,
+                    const float* __restrict__ qn, const float* __restrict__ qmax, int N, int T64, int K,
+                    float eps_rel, uint2* __restrict__ surv, int* __restrict__ surv_cnt) {
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* sA_hi = smem;                                   // [KC][128][8] bf16   32 KB
-  unsigned char* sA_lo = sA_hi + 2 * TILE_BYTES;                 //                      32 KB
-  unsigned char* sB = sA_lo + 2 * TILE_BYTES;                    // 2 stages x (hi 16 KB + lo 16 KB)
-  float* s_qn = reinterpret_cast<float*>(sB + 4 * TILE_BYTES);   // [ROUND_COLS]
-  uint2* s_list = reinterpret_cast<uint2*>(s_qn + ROUND_COLS);   // [128][LCAP] (approximate distance bits, index)
-  int* s_cnt = reinterpret_cast<int*>(s_list + QROWS * LCAP);    // [128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_cnt + QROWS);   // [0..1] full, [2..3] empty, [4] A full, [5] round done, [6] A free
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 7);
+  unsigned char* sA_hi = smem;                                   // [ND][KC][128][8] bf16
+  unsigned char* sA_lo = sA_hi + ND * 2 * TILE_BYTES;
+  unsigned char* sB = sA_lo + ND * 2 * TILE_BYTES;               // 2 stages x 16 KB: stage 0 = hi tiles, 1 = lo tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * TILE_BYTES);
+  uint64_t* a_full = bars;                                       // [1]
+  uint64_t* b_full = bars + 1;                                   // [2]
+  uint64_t* b_empty = bars + 3;                                  // [2]
+  uint64_t* slot_full = bars + 5;                                // [NSLOT]
+  uint64_t* slot_empty = bars + 5 + NSLOT;                       // [NSLOT]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5 + 2 * NSLOT);
 
   const int b = blockIdx.y, qt = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rows_pad = T64 * TR;
-  const unsigned char* obj_hi = reinterpret_cast<const unsigned char*>(ghi) + (size_t)b * T64 * nd * TILE_BYTES;
-  const unsigned char* obj_lo = reinterpret_cast<const unsigned char*>(glo) + (size_t)b * T64 * nd * TILE_BYTES;
+  const unsigned char* obj_hi = reinterpret_cast<const unsigned char*>(ghi) + (size_t)b * T64 * ND * TILE_BYTES;
+  const unsigned char* obj_lo = reinterpret_cast<const unsigned char*>(glo) + (size_t)b * T64 * ND * TILE_BYTES;
   const float* qb = qn + (size_t)b * rows_pad;
+  const int items = 2 * T64;                                     // two sweeps over the 64-candidate sub-tiles
 
-  if (warp == 0) {   // TMEM: all 512 columns (one CTA per SM)
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
-                 "r"(512)
+                 "r"(NSLOT * TR)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-#pragma unroll
-    for (int i = 0; i < 7; ++i) mbar_init(bars + i, 1);
+    mbar_init(a_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(slot_full + i, 1); mbar_init(slot_empty + i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  s_cnt[tid] = 0;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *s_tmem;
 
-  const int i_row = qt * QROWS + tid;                 // this thread's query row (TMEM lane tid)
-  const bool row_ok = i_row < N;
-  const float qi = qb[min(i_row, rows_pad - 1)];
-  const float eps2 = 2.0f * eps_rel * sqrtf(fmaxf(qi, 0.0f) * __ldg(qmax + b)) + 1e-30f;
-  float thr = INFINITY;                               // running upper bound on the K-th smallest (d~ - qi)
-  int cnt = 0;
-  bool overflow = false;
-  float m[SLOTS];                                     // running slot minima of d~ - qi
-#pragma unroll
-  for (int i = 0; i < SLOTS; ++i) m[i] = INFINITY;
-
-  const uint32_t idesc = umma_idesc(QROWS, TR);
-  const int nsub_total = T64;                         // 64-candidate sub-tiles
-  int it = 0;                                         // global sub-tile counter (pipeline phase tracking)
-  int a_loads = 0;                                    // query-block loads so far (thread 0 only)
-  for (int sub0 = 0, round = 0; sub0 < nsub_total; sub0 += ROUND_COLS / TR, ++round) {
-    const int nsub = min(ROUND_COLS / TR, nsub_total - sub0);
-    const int col0 = sub0 * TR;
-    // candidate norms of this round
-    for (int c = tid; c < nsub * TR; c += THREADS) s_qn[c] = qb[col0 + c];
-
-    if (tid == 0) {
-      for (int h = 0; h < nd; ++h) {
-        if (round == 0 || nd > 1) {
-          // query block of this d-half: two 64-row tiles -> [KC][128][8]   (64 bulk copies of 1 KB)
-          if (a_loads > 0) {                          // every MMA that reads the old block has retired
-            umma_commit(bars + 6);
-            mbar_wait(bars + 6, (a_loads - 1) & 1);
+  if (warp == 4) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      mbar_expect_tx(a_full, ND * 4 * TILE_BYTES);
+      for (int h = 0; h < ND; ++h)
+        for (int hh = 0; hh < 2; ++hh) {
+          const size_t src = ((size_t)(2 * qt + hh) * ND + h) * TILE_BYTES;
+          for (int kc = 0; kc < KC; ++kc) {   // two 64-row tiles -> [KC][128][8]
+            bulk_g2s(sA_hi + h * 2 * TILE_BYTES + kc * 2048 + hh * 1024, obj_hi + src + kc * 1024, 1024, a_full);
+            bulk_g2s(sA_lo + h * 2 * TILE_BYTES + kc * 2048 + hh * 1024, obj_lo + src + kc * 1024, 1024, a_full);
           }
-          mbar_expect_tx(bars + 4, 4 * TILE_BYTES);
-          for (int hh = 0; hh < 2; ++hh) {
-            const size_t src = ((size_t)(2 * qt + hh) * nd + h) * TILE_BYTES;
-            for (int kc = 0; kc < KC; ++kc) {
-              bulk_g2s(sA_hi + kc * 2048 + hh * 1024, obj_hi + src + kc * 1024, 1024, bars + 4);
-              bulk_g2s(sA_lo + kc * 2048 + hh * 1024, obj_lo + src + kc * 1024, 1024, bars + 4);
+        }
+      int n = 0;                                                 // uses of each stage so far
+      for (int j = 0; j < items; ++j) {
+        const int sub = j < T64 ? j : j - T64;
+        for (int h = 0; h < ND; ++h, ++n) {
+          const size_t src = ((size_t)sub * ND + h) * TILE_BYTES;
+          if (n >= 1) mbar_wait(b_empty + 0, (n - 1) & 1);
+          mbar_expect_tx(b_full + 0, TILE_BYTES);
+          bulk_g2s(sB, obj_hi + src, TILE_BYTES, b_full + 0);
+          if (n >= 1) mbar_wait(b_empty + 1, (n - 1) & 1);
+          mbar_expect_tx(b_full + 1, TILE_BYTES);
+          bulk_g2s(sB + TILE_BYTES, obj_lo + src, TILE_BYTES, b_full + 1);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(QROWS, TR);
+      mbar_wait(a_full, 0);
+      int n = 0;
+      for (int j = 0; j < items; ++j) {
+        const int slot = j % NSLOT, use = j / NSLOT;
+        if (use >= 1) mbar_wait(slot_empty + slot, (use - 1) & 1);   // the epilogue has drained this slot
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(slot * TR);
+        for (int h = 0; h < ND; ++h, ++n) {
+          const uint32_t ah = smem_u32(sA_hi + h * 2 * TILE_BYTES), al = smem_u32(sA_lo + h * 2 * TILE_BYTES);
+          const uint32_t bh = smem_u32(sB), bl = bh + TILE_BYTES;
+          mbar_wait(b_full + 0, n & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < DK / 16; ++k)                      // hi * hi
+            umma_bf16(d_tmem, umma_desc(ah + k * 2 * 2048, 2048, 128), umma_desc(bh + k * 2 * 1024, 1024, 128), idesc,
+                      (h | k) != 0);
+#pragma unroll
+          for (int k = 0; k < DK / 16; ++k)                      // lo * hi
+            umma_bf16(d_tmem, umma_desc(al + k * 2 * 2048, 2048, 128), umma_desc(bh + k * 2 * 1024, 1024, 128), idesc, 1);
+          umma_commit(b_empty + 0);
+          mbar_wait(b_full + 1, n & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < DK / 16; ++k)                      // hi * lo
+            umma_bf16(d_tmem, umma_desc(ah + k * 2 * 2048, 2048, 128), umma_desc(bl + k * 2 * 1024, 1024, 128), idesc, 1);
+          umma_commit(b_empty + 1);
+        }
+        umma_commit(slot_full + slot);
+      }
+    }
+  } else {
+    // ============================ epilogue: thread = TMEM lane = query row ============================
+    const int i_row = qt * QROWS + tid;
+    const bool row_ok = i_row < N;
+    const float qi = qb[min(i_row, rows_pad - 1)];
+    const float eps2 = 2.0f * eps_rel * sqrtf(fmaxf(qi, 0.0f) * __ldg(qmax + b)) + 1e-30f;
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float m[SLOTS];                                              // slot minima of d~ - qi (slot = column mod 64)
+#pragma unroll
+    for (int i = 0; i < SLOTS; ++i) m[i] = INFINITY;
+    auto wait_slot = [&](int j) {
+      mbar_wait(slot_full + (j % NSLOT), (j / NSLOT) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+    auto release_slot = [&](int j) {
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(slot_empty + (j % NSLOT));
+    };
+    // sweep 1: slot minima over every candidate
+    for (int j = 0; j < T64; ++j) {
+      wait_slot(j);
+      const float4* q4p = reinterpret_cast<const float4*>(qb + j * TR);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tmem_ld32(t_row + (uint32_t)((j % NSLOT) * TR + half * 32), v);
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 q4 = __ldg(q4p + half * 8 + i4);          // warp-uniform address: one broadcast transaction
+          const int o = half * 32 + 4 * i4;
+          m[o] = fminf(m[o], fmaf(-2.0f, v[4 * i4], q4.x));
+          m[o + 1] = fminf(m[o + 1], fmaf(-2.0f, v[4 * i4 + 1], q4.y));
+          m[o + 2] = fminf(m[o + 2], fmaf(-2.0f, v[4 * i4 + 2], q4.z));
+          m[o + 3] = fminf(m[o + 3], fmaf(-2.0f, v[4 * i4 + 3], q4.w));
+        }
+      }
+      release_slot(j);
+    }
+    sort_regs<SLOTS>(m);
+    float tau = m[0];
+#pragma unroll
+    for (int i = 1; i < SLOTS; ++i) tau = (i == K - 1) ? m[i] : tau;   // >= K distinct candidates lie at or below it
+    // sweep 2: survivors under the final threshold.  The TMEM loads are .sync.aligned: every lane runs the same
+    // loop; rows past N collect nothing.  Padding columns carry q = +inf and never pass a finite limit; NaN
+    // distances always pass.
+    const float lim = tau + eps2;
+    uint2* my_list = surv + ((size_t)b * N + min(i_row, N - 1)) * LCAP;
+    int cnt = 0;
+    for (int j = T64; j < items; ++j) {
+      wait_slot(j);
+      const int jb = (j - T64) * TR;
+      const float4* q4p = reinterpret_cast<const float4*>(qb + jb);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tmem_ld32(t_row + (uint32_t)((j % NSLOT) * TR + half * 32), v);
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 q4 = __ldg(q4p + half * 8 + i4);
+          const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = half * 32 + 4 * i4 + u;
+            const float dapp = fmaf(-2.0f, v[4 * i4 + u], qv[u]);
+            if (row_ok && !(dapp > lim)) {
+              if (cnt < LCAP) my_list[cnt] = make_uint2(__float_as_uint(dapp), (unsigned)(jb + i));
+              ++cnt;
             }
           }
-          mbar_wait(bars + 4, a_loads & 1);
-          ++a_loads;
-        }
-        auto load = [&](int s, int iter) {
-          const int st = iter & 1;
-          if (iter >= 2) mbar_wait(bars + 2 + st, ((iter >> 1) - 1) & 1);   // MMAs that read this stage are done
-          mbar_expect_tx(bars + st, 2 * TILE_BYTES);
-          const size_t src = ((size_t)(sub0 + s) * nd + h) * TILE_BYTES;
-          bulk_g2s(sB + st * 2 * TILE_BYTES, obj_hi + src, TILE_BYTES, bars + st);
-          bulk_g2s(sB + st * 2 * TILE_BYTES + TILE_BYTES, obj_lo + src, TILE_BYTES, bars + st);
-        };
-        load(0, it);
-        for (int s = 0; s < nsub; ++s) {
-          const int iter = it + s, st = iter & 1;
-          if (s + 1 < nsub) load(s + 1, iter + 1);
-          mbar_wait(bars + st, (iter >> 1) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t d_tmem = tmem_base + (uint32_t)(s * TR);
-          const uint32_t bh = smem_u32(sB + st * 2 * TILE_BYTES), bl = bh + TILE_BYTES;
-          const uint32_t ah = smem_u32(sA_hi), al = smem_u32(sA_lo);
-#pragma unroll
-          for (int term = 0; term < 3; ++term) {
-            const uint32_t a0 = term == 2 ? al : ah, b0 = term == 1 ? bl : bh;
-#pragma unroll
-            for (int k = 0; k < DK / 16; ++k)
-              umma_bf16(d_tmem, umma_desc(a0 + k * 2 * 2048, 2048, 128), umma_desc(b0 + k * 2 * 1024, 1024, 128),
-                        idesc, (h | term | k) != 0);
-          }
-          umma_commit(bars + 2 + st);                 // stage free when these MMAs retire
-          if (s == nsub - 1 && h == nd - 1) umma_commit(bars + 5);   // round complete
-        }
-        it += nsub;
-      }
-    }
-    __syncthreads();                                  // s_qn visible; (tid 0 has issued everything)
-    mbar_wait(bars + 5, round & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    // ---- epilogue: thread = TMEM lane = query row
-    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const float4* s_qn4 = reinterpret_cast<const float4*>(s_qn);
-    uint2* my_list = s_list + tid * LCAP;
-    {
-      // pass 1: running slot minima over every candidate seen so far (slot = column mod 64)
-      for (int c = 0; c < nsub * TR; c += 64) {
-        float v[64];
-        tmem_ld64(t_row + (uint32_t)c, v);
-#pragma unroll
-        for (int i4 = 0; i4 < 16; ++i4) {
-          const float4 q4 = s_qn4[(c >> 2) + i4];
-          m[4 * i4] = fminf(m[4 * i4], fmaf(-2.0f, v[4 * i4], q4.x));
-          m[4 * i4 + 1] = fminf(m[4 * i4 + 1], fmaf(-2.0f, v[4 * i4 + 1], q4.y));
-          m[4 * i4 + 2] = fminf(m[4 * i4 + 2], fmaf(-2.0f, v[4 * i4 + 2], q4.z));
-          m[4 * i4 + 3] = fminf(m[4 * i4 + 3], fmaf(-2.0f, v[4 * i4 + 3], q4.w));
         }
       }
-      float ms[SLOTS];
-#pragma unroll
-      for (int i = 0; i < SLOTS; ++i) ms[i] = m[i];
-      sort_regs<SLOTS>(ms);
-      float tau = ms[0];
-#pragma unroll
-      for (int i = 1; i < SLOTS; ++i) tau = (i == K - 1) ? ms[i] : tau;
-      thr = fminf(thr, tau);           // >= K distinct candidates lie at or below it
+      release_slot(j);
     }
-    if (cnt > 24 && !overflow) {       // survivors of earlier rounds under the tightened threshold
-      const float lim2 = thr + eps2;
-      int w = 0;
-      for (int e = 0; e < cnt; ++e) {
-        const uint2 ev = my_list[e];
-        if (!(__uint_as_float(ev.x) > lim2)) { my_list[w] = ev; ++w; }
-      }
-      cnt = w;
-    }
-    // pass 2 over the resident inner products: survivors under the tightest threshold known.  The
-    // TMEM loads are .sync.aligned: every lane runs the same loop; rows past N collect nothing.
-    // Padding columns carry q = +inf and never pass a finite limit; NaN distances always pass.
-    const float lim = row_ok ? thr + eps2 : -INFINITY;
-    for (int c = 0; c < nsub * TR; c += 64) {
-      float v[64];
-      tmem_ld64(t_row + (uint32_t)c, v);
-      const int jb = col0 + c;
-      bool room = true;
-#pragma unroll
-      for (int i4 = 0; i4 < 16; ++i4) {
-        if ((i4 & 3) == 0) {                        // 16 columns append at most 16: one capacity check
-          room = cnt <= LCAP - 16;
-          overflow |= !room;
-        }
-        const float4 q4 = s_qn4[(c >> 2) + i4];
-        const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = 4 * i4 + u;
-          const float dapp = fmaf(-2.0f, v[i], qv[u]);
-          if (room && !(dapp > lim)) {
-            my_list[cnt] = make_uint2(__float_as_uint(dapp), (unsigned)(jb + i));
-            ++cnt;
-          }
-        }
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();                                  // TMEM / s_qn free for the next round
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (row_ok) surv_cnt[(size_t)b * N + i_row] = cnt <= LCAP ? cnt : -1;   // -1: refine scans every candidate
   }
-  // final threshold is the tightest: drop survivors of earlier rounds that no longer qualify
-  {
-    const float lim = thr + eps2;
-    uint2* my_list = s_list + tid * LCAP;
-    int w = 0;
-    for (int e = 0; e < cnt; ++e) {
-      const uint2 ev = my_list[e];
-      if (!(__uint_as_float(ev.x) > lim)) { my_list[w] = ev; ++w; }
-    }
-    cnt = w;
-  }
-  if (overflow) cnt = -1;                            // refine scans every candidate for this row
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-  if (row_ok) {
-    surv_cnt[(size_t)b * N + i_row] = cnt;
-    const uint4* src = reinterpret_cast<const uint4*>(s_list + tid * LCAP);
-    uint4* dst = reinterpret_cast<uint4*>(surv + ((size_t)b * N + i_row) * LCAP);
-    const int nv = cnt > 0 ? (cnt + 1) / 2 : 0;      // (approximate distance, index) pairs, 16 bytes = 2 entries
-    for (int e = 0; e < nv; ++e) dst[e] = src[e];
-  }
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NSLOT * TR) : "memory");
 }
+
+static size_t smem_bytes2(int nd) { return (size_t)nd * 4 * TILE_BYTES + 2 * TILE_BYTES + (5 + 2 * NSLOT) * 8 + 16; }
 
 // ---- refine: warp per query row.  The survivors' FP32 rows are fetched cooperatively (a warp reads
 // one 512-byte row with four coalesced 128-byte requests; all rows of a batch in flight) into
@@ -535,26 +538,20 @@ kf_refine_kernel(const float* __restrict__ feat, const float* __restrict__ qn, c
   }
 }
 
-static size_t smem_bytes() {
-  return (size_t)8 * TILE_BYTES + ROUND_COLS * sizeof(float) + (size_t)QROWS * LCAP * sizeof(uint2) +
-         QROWS * sizeof(int) + 7 * sizeof(uint64_t) + 16;
-}
-
 }  // namespace tc
 
 // T64: number of 64-row tiles, rounded up to an even count (a query block is two tiles).
 static int kf_tc_tiles(int N) { return 2 * ((N + 127) / 128); }
 
-// D = 256 runs two d-halves that accumulate into the same TMEM columns, so every candidate of the
-// object must be resident at once: N <= 512.
 bool knn_feat_tc_supported(int N, int D, int K) {
   // below ~128 points the all-FP32 kernel wins (measured: N = 64, D = 256: 0.05 vs 0.09 ms at B = 128)
-  return (D == 128 || (D == 256 && N <= tc::ROUND_COLS)) && K <= 64 && N >= 128 && N <= 65535;
+  if (!(K <= 64 && N >= 128 && N <= 65535)) return false;
+  return D == 128 || D == 256;
 }
 
 size_t knn_feat_tc_workspace_bytes(int B, int N) {
   const size_t T64 = kf_tc_tiles(N);
-  const size_t nd = N <= tc::ROUND_COLS ? 2 : 1;   // the query has no D: size for the widest supported case
+  const size_t nd = 2;                             // the query has no D: size for the widest supported case
   return (size_t)B * T64 * nd * tc::TILE_BYTES * 2 + (size_t)B * T64 * tc::TR * sizeof(float) +
          (size_t)B * sizeof(float) + (size_t)B * N * (tc::LCAP * sizeof(uint2) + sizeof(int)) + 1024;
 }
@@ -580,12 +577,21 @@ int knn_feat_tc_launch(const float* feat, int B, int N, int D, int K, int drop, 
   HSP_LAUNCH_CHECK();
   kf_split_kernel<<<dim3((T64 * TR * (D / 8) + 255) / 256, B), 256, 0, st>>>(feat, N, D, T64, hi, lo);
   HSP_LAUNCH_CHECK();
-  const size_t smem = smem_bytes();
-  if (cudaFuncSetAttribute(knn_feat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-      cudaSuccess)
-    return HSP_ELAUNCH;
-  knn_feat_tc_kernel<<<dim3(T64 / 2, B), THREADS, smem, st>>>(hi, lo, qn, qmax, N, T64, K, nd, eps_rel, surv,
-                                                            surv_cnt);
+  if (nd == 1) {
+    const size_t smem = smem_bytes2(1);
+    if (cudaFuncSetAttribute(knn_feat_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return HSP_ELAUNCH;
+    knn_feat_tc2_kernel<1><<<dim3(T64 / 2, B), THREADS2, smem, st>>>(hi, lo, qn, qmax, N, T64, K, eps_rel, surv,
+                                                                   surv_cnt);
+  } else {
+    const size_t smem = smem_bytes2(2);
+    if (cudaFuncSetAttribute(knn_feat_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return HSP_ELAUNCH;
+    knn_feat_tc2_kernel<2><<<dim3(T64 / 2, B), THREADS2, smem, st>>>(hi, lo, qn, qmax, N, T64, K, eps_rel, surv,
+                                                                   surv_cnt);
+  }
   HSP_LAUNCH_CHECK();
   const dim3 rg((N + RF_WARPS - 1) / RF_WARPS, B);
 #define HSP_RF(NL_, D_)                                                                                   \

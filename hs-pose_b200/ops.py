@@ -120,7 +120,7 @@ def knn_feat(feat, k, drop_first=1, want64=False, want32=True):
         i32 = torch.empty(B, N, k, dtype=torch.int32, device=feat.device) if want32 else None
         _call("hsp_knn_feat", _p(feat), B, N, D, k, drop_first, _p(i64), _p(i32), _p(ws),
               ws.numel(), _stream())
-        if N >= 128 and (D == 128 or (D == 256 and N <= 512)) and k + drop_first <= 64:
+        if N >= 128 and D in (128, 256) and k + drop_first <= 64:
             global _launches
             _launches += 2   # tensor-core path: norm, split, filter, refine (4 kernels instead of 2)
     return i64, i32

@@ -108,13 +108,40 @@ def test_knn_feat_golden_and_oracle(cuda, golden):
 
 
 @pytest.mark.parametrize("B,N,D,k", [(2, 1028, 128, 20), (2, 257, 256, 20), (3, 64, 256, 8),
-                                     (1, 300, 128, 32), (1, 70, 32, 4)])
+                                     (1, 300, 128, 32), (1, 70, 32, 4), (2, 1028, 256, 20), (1, 700, 256, 8)])
 def test_knn_feat_vs_oracle(cuda, B, N, D, k):
     ops = _ops()
     g = torch.Generator().manual_seed(N + D + k)
     f = torch.relu(torch.randn(B, N, D, generator=g) + 1.0)
     got = ops.knn_feat(f.to(cuda), k, want64=True)[0].cpu().numpy()
     assert np.array_equal(got, co.neighbor_index(f.numpy(), k))
+
+
+def test_knn_feat_vs_reference_formulation_on_this_gpu(cuda):
+    """The reference's own expression (gcn3d.py:15-24: bmm + norms + topk) evaluated by cuBLAS ON THE B200 with both
+    allow_tf32 switches off (SURVEY §7 hard part 4), against K2: the two orders of fp32 summation agree on >= 97 % of
+    the rows, and where a row differs, every neighbour either side picked lies within the fp32 rounding envelope
+    of the K-th distance (|d_i - d_K| <= 2^-14 |f_i||f_j|, the bound K2-TC itself uses)."""
+    ops = _ops()
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for (B, N, D, k) in ((4, 1028, 128, 20), (4, 257, 256, 20)):
+            g = torch.Generator().manual_seed(N + D)
+            f = torch.relu(torch.randn(B, N, D, generator=g) + 0.5).to(cuda)
+            ref = to.neighbor_index(f, k)                                   # cuBLAS bmm order on this GPU
+            got = ops.knn_feat(f, k, want64=True)[0]
+            same_rows = (got == ref).all(dim=2)
+            assert same_rows.float().mean().item() >= 0.97
+            d64 = to.pairwise_neighbor_dist(f.double())                     # the same expression in fp64
+            kth = d64.gather(2, got[..., -1:])
+            nrm = f.double().norm(dim=2)
+            env = 2.0 ** -14 * nrm[:, :, None] * nrm.max(dim=1)[0][:, None, None] * 2
+            for idx in (got, ref):
+                assert bool((d64.gather(2, idx) <= kth + env).all())
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
 
 
 # ----------------------------------------------------------------- K3 / K4
