@@ -33,8 +33,7 @@ def bn_points(bn: nn.BatchNorm1d, x_bnc, relu=False):
     shape = x_bnc.shape
     x2 = x_bnc.reshape(-1, shape[-1])
     if bn.training and mixed_precision() and x2.is_cuda and shape[-1] % 8 == 0 and x2.shape[0] > 1:
-        if bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += 1
+        ops.bump_counter(bn.num_batches_tracked)
         y = ops.bn_relu(x2, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
                         bn.momentum, relu)
     else:
@@ -96,8 +95,7 @@ def conv_bn_relu_points(conv: nn.Conv1d, bn: nn.BatchNorm1d, x_bnc, relu=True):
         w = conv.weight[:, :, 0]
         if pad_in:
             w = F.pad(w, (0, pad_in))
-        if bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += 1
+        ops.bump_counter(bn.num_batches_tracked)
         z = ops.linear_bn_relu(x_bnc.reshape(-1, shape[-1]), w, conv.bias, bn.weight, bn.bias,
                                bn.running_mean, bn.running_var, bn.eps, bn.momentum, relu)
         return z.view(*shape[:-1], conv.out_channels)
@@ -126,8 +124,7 @@ def multi_conv_bn_relu_points(pairs, x_bnc):
         pad_in = shape[-1] - conv.in_channels
         if pad_in:
             w = F.pad(w, (0, pad_in))
-        if bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += 1
+        ops.bump_counter(bn.num_batches_tracked)
         blocks.append((w, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
                        bn.momentum, True))
     outs = ops.multi_linear_bn_relu(x_bnc.reshape(-1, shape[-1]), blocks)
@@ -253,9 +250,11 @@ class FaceRecon(nn.Module):
                 conv1d_out = seq_points(self.conv1d_block, feat_pad if mixed else feat)   # (bs, N, 256)
             recon = seq_points(self.recon_head, conv1d_out)                            # (bs, N, 3)
             face = self._face_head(f_global, conv1d_out, vertices)                     # (bs, N, 30)
+            ops.flush_counters()
             return recon, face, feat
         if joint and all(fused_block_ok(c, b, feat_pad) for c, b in joint):
             self.joint_out = multi_conv_bn_relu_points(joint, feat_pad)
+        ops.flush_counters()
         return None, None, feat
 
     def _face_head(self, f_global, conv1d_out, vertices):
@@ -277,8 +276,7 @@ class FaceRecon(nn.Module):
         if bn0.training and n > 1:
             # face_head[0..2] = conv -> BN -> ReLU as one K6/K6b node; the f_global block enters the GEMM
             # epilogue as a per-object bias (no (bs, N, 512) broadcast add)
-            if bn0.num_batches_tracked is not None:
-                bn0.num_batches_tracked += 1
+            ops.bump_counter(bn0.num_batches_tracked)
             z = ops.linear_bn_relu(tail.view(bs * n, -1), F.pad(w[:, cg:], (0, pad)), None, bn0.weight, bn0.bias,
                                    bn0.running_mean, bn0.running_var, bn0.eps, bn0.momentum, True,
                                    bias_rows=per_obj.contiguous(), rows_per_group=n)

@@ -114,6 +114,7 @@ class HSPose(nn.Module):
 
     # ---- K8: the whole 19-term loss graph as two launches each way (ops.fused_losses)
     fused_losses = True    # set False to evaluate the losses with the tensor-algebra modules of losses.py
+    _loss_mask = {}        # (selection, device) -> 0/1 vector over ops.LOSS_TERMS
 
     def _fused_losses_ok(self, PC, recon):
         return (self.fused_losses and PC.is_cuda and recon is not None and self.train_stage == 'PoseNet_only'
@@ -134,7 +135,16 @@ class HSPose(nn.Module):
                                  "recon_point_s", "recon_point_self")} if "recon" in g else {}
         geo = {"geo_point": t["geo_point"]} if "geo" in g else {}
         prop = {k: t[k] for k in ("Prop_pm", "Prop_sym_recon", "Prop_sym_rt")} if "prop" in g else {}
-        return {'fsnet_loss': fs, 'recon_loss': rec, 'geo_loss': geo, 'prop_loss': prop}
+        out = ops.LossGroups(fsnet_loss=fs, recon_loss=rec, geo_loss=geo, prop_loss=prop)
+        # the sum of the selected terms as ONE masked reduction of the term vector (+ Chamfer)
+        sel = [1.0 if any(name in grp for grp in (fs, rec, geo, prop)) else 0.0 for name in ops.LOSS_TERMS]
+        mask = self._loss_mask.get((tuple(sel), t.vector.device))
+        if mask is None:
+            mask = self._loss_mask[(tuple(sel), t.vector.device)] = torch.tensor(sel, device=t.vector.device)
+        out.total = (t.vector * mask).sum()
+        if 'Chamfer' in fs:
+            out.total = out.total + fs['Chamfer'].reshape(()).float()
+        return out
 
     def data_augment(self, PC, gt_R, gt_t, gt_s, mean_shape, sym, aug_bb, aug_rt_t, aug_rt_r,
                      model_point, nocs_scale, obj_ids, check_points=False):

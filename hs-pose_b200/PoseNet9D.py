@@ -9,6 +9,7 @@ import torch.nn as nn
 from .FaceRecon import FaceRecon
 from .PoseR import Rot_green, Rot_red
 from .PoseTs import Pose_Ts
+from . import ops
 from .flags import FLAGS
 
 
@@ -54,6 +55,7 @@ class PoseNet9D(nn.Module):
 
         feat_for_ts = torch.cat([feat, centred], dim=2) if feat_pad is None else feat_pad
         T, s = self.ts.forward_points(feat_for_ts, joint[2])
+        ops.flush_counters()      # BatchNorm num_batches_tracked of every fused block above: one multi-tensor add
         Pred_T = T.float() + mean[:, 0, :]
         Pred_s = s.float()
         return recon, face_normal, face_dis, face_f, p_green_R, p_red_R, f_green_R, f_red_R, Pred_T, Pred_s

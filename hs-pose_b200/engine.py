@@ -124,7 +124,9 @@ class TrainStep:
         try:
             with self._tf32_scope(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
                 _, losses = self.model(**batch, do_loss=True)
-            total = sum(v.reshape(()).float() for grp in losses.values() for v in grp.values())
+            total = getattr(losses, "total", None)      # HSPose's fused loss path sums its terms in one reduction
+            if total is None:
+                total = sum(v.reshape(()).float() for grp in losses.values() for v in grp.values())
             self.flat.zero()
             if self._overlap:
                 total.backward()                  # gradients accumulate into the flat views as they arrive

@@ -922,7 +922,35 @@ def fused_losses(weights, face, recon, p_green, p_red, f_green, f_red, pred_T, p
     """K8 -> dict {term name: scalar} over LOSS_TERMS.  `weights`: the 17 floats of LOSS_WEIGHT_FLAGS."""
     terms = _FusedLosses.apply(tuple(float(x) for x in weights), face, recon, p_green, p_red, f_green, f_red,
                                pred_T, pred_s, PC, gt_R, gt_t, gt_s, mean_shape, sym, obj_id)
-    return {name: terms[i] for i, name in enumerate(LOSS_TERMS)}
+    out = LossTerms(zip(LOSS_TERMS, terms.unbind(0)))      # one autograd node for the 19 views
+    out.vector = terms
+    return out
+
+
+class LossTerms(dict):
+    """{term name: scalar}; `.vector` is the (19,) tensor the scalars are views of (one reduction sums them)."""
+    vector = None
+
+
+class LossGroups(dict):
+    """The reference's 4-key loss dict; `.total` (optional) is the sum of every term in it, computed with one
+    reduction instead of one add per term — what a train loop that only needs the total should use."""
+    total = None
+
+
+# BatchNorm `num_batches_tracked` of the fused BN paths: one multi-tensor add per forward instead of one launch each
+_pending_counters = []
+
+
+def bump_counter(t):
+    if t is not None:
+        _pending_counters.append(t)
+
+
+def flush_counters():
+    if _pending_counters:
+        torch._foreach_add_(_pending_counters, 1)
+        _pending_counters.clear()
 
 
 # ------------------------------------------------------------ K10: augmentation

@@ -471,6 +471,31 @@ def test_fused_loss_kernel_matches_loss_modules(cuda):
             assert err <= rel * ga.abs().max().item() + 1e-9, (gname, name, err, ga.abs().max().item())
 
 
+@pytest.mark.parametrize("groups", [("fsnet", "recon", "geo", "prop"), ("fsnet", "geo")])
+def test_loss_total_is_the_sum_of_the_returned_terms(cuda, groups):
+    """HSPose's fused loss path also returns `.total` (one masked reduction of the term vector + Chamfer) for train
+    loops that only need the sum (engine.TrainStep): same value and same gradients as adding the dict entries one by
+    one the way engine/train.py:137-149 does; the 4-key dict itself is unchanged."""
+    from hspose_b200.HSPose import HSPose
+    F = _flags()
+    F.train, F.gcn_n_num = 1, 20
+    net = fill_params(HSPose("PoseNet_only", chamfer_w=1.0, loss_groups=groups)).to(cuda).train()
+    batch = {k: v.to(cuda) for k, v in synth_batch(4, 1028, seed=5, train=True).items()}
+    grads = []
+    for use_total in (True, False):
+        torch.manual_seed(7)
+        net.zero_grad(set_to_none=True)
+        _, losses = net(**batch, do_loss=True)
+        assert set(losses) == {"fsnet_loss", "recon_loss", "geo_loss", "prop_loss"}
+        manual = sum(v.reshape(()).float() for grp in losses.values() for v in grp.values())
+        assert losses.total is not None
+        assert abs(float(losses.total) - float(manual)) <= 1e-5 * abs(float(manual))
+        (losses.total if use_total else manual).backward()
+        grads.append(torch.cat([p.grad.flatten() for p in net.parameters() if p.grad is not None]))
+    rel = float((grads[0] - grads[1]).norm() / grads[1].norm())
+    assert rel <= 1e-4, rel        # fp32 float-atomic noise between two runs of the same step is ~1e-6
+
+
 @pytest.mark.parametrize("tag,probs", [
     ("all", dict(aug_pc_pro=1.0, aug_rt_pro=1.0, aug_bb_pro=1.0, aug_bc_pro=1.0)),
     ("default", dict(aug_pc_pro=0.2, aug_rt_pro=0.3, aug_bb_pro=0.3, aug_bc_pro=0.3))])
