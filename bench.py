@@ -127,6 +127,10 @@ def _alg_bytes(name, a, train=True):
         dt, B, N, k, S, C = a[:6]
         e = 2 if dt == 1 else 4
         return B * (12 * N + 4 * N * k + e * N * (S + 1) * C + N * S * C + 4 * N * C + 4 * N * (S + 1) * C)
+    if name == "hsp_graph_conv_bwd_obj":   # ints: p_dtype, B, N, k, S, C, gp_dtype, ws
+        dt, B, N, k, S, C, gdt = a[:7]
+        e, eo = (2 if dt == 1 else 4), (2 if gdt == 1 else 4)
+        return B * (12 * N + 4 * N * k + e * N * (S + 1) * C + N * S * C + 4 * N * C + eo * N * (S + 1) * C)
     if name == "hsp_surface_conv_fwd" or name == "hsp_surface_conv_bwd":
         B, N, k, S, C = a[:5]
         return B * (12 * N + 4 * N * k + 4 * N * C)
@@ -171,7 +175,7 @@ def _alg_flops(name, a):
     if name == "hsp_gemm_bf16":
         lda, amn, ldb, bmn, M, N, K = a[:7]
         return 2.0 * M * N * K
-    if name in ("hsp_graph_conv_fwd", "hsp_graph_conv_bwd"):
+    if name in ("hsp_graph_conv_fwd", "hsp_graph_conv_bwd", "hsp_graph_conv_bwd_obj"):
         dt, B, N, k, S, C = a[:6]
         per = 8.0 if name.endswith("fwd") else 8.0 / k      # theta (3 FMA) + product + max per (n,k,s,c); bwd: winners only
         return B * N * k * S * C * per
@@ -190,11 +194,13 @@ def _alg_flops(name, a):
 def _gather_bytes(name, a):
     """SM <-> L2 bytes the ALGORITHM needs (every gathered row counted once per use): the gather kernels'
     real yardstick ('the gather is L2-bandwidth-, not HBM-bound')."""
-    if name in ("hsp_graph_conv_fwd", "hsp_graph_conv_bwd"):
+    if name in ("hsp_graph_conv_fwd", "hsp_graph_conv_bwd", "hsp_graph_conv_bwd_obj"):
         dt, B, N, k, S, C = a[:6]
         e = 2 if dt == 1 else 4
         if name.endswith("fwd"):
             return B * N * k * S * C * e
+        if name.endswith("obj"):                  # winners only: P read, arg-max byte, 16-byte pair record per 32 channels
+            return B * N * S * C * (e + 1) + B * N * S * (C // 32) * k * 16
         return B * N * S * C * (e + 4 + 1)       # winners only: P read, gP atomic, arg-max byte
     if name in ("hsp_orl_global_fwd",):
         B, N, C, k = a[:4]
@@ -223,7 +229,10 @@ def kernel_breakdown(records, steps):
 def _ncu_key(name, a):
     if name == "hsp_graph_conv_bwd":
         dt, B, N, k, S, C = a[:6]
-        return "graph_conv_bwd_kernel", f"({min(B * ((N + 7) // 8), 592)}, 1, {(C + 127) // 128})"
+        return "graph_conv_bwd2_kernel", f"({min(B * ((N + 7) // 8), 592)}, 1, {(C + 127) // 128})"
+    if name == "hsp_graph_conv_bwd_obj":
+        dt, B, N, k, S, C = a[:6]
+        return "graph_conv_bwd_obj_kernel", f"({C // 32}, {S + 1}, {B})"
     if name == "hsp_graph_conv_fwd":
         dt, B, N, k, S, C = a[:6]
         pairs = C // 2
@@ -231,8 +240,8 @@ def _ncu_key(name, a):
         return "graph_conv_fwd2_kernel", f"({(N + 7) // 8}, {B}, {(pairs + lanes - 1) // lanes})"
     if name == "hsp_knn_feat":
         B, N, D, k = a[:4]
-        if D == 128:
-            return "tc::knn_feat_tc_kernel", f"({(N + 127) // 128}, {B}, 1)"
+        if D in (128, 256) and N >= 128:
+            return "tc::knn_feat_tc2_kernel", f"({(N + 127) // 128}, {B}, 1)"
         return "knn_feat_kernel", f"({(N + 63) // 64}, {B}, 1)"
     if name == "hsp_surface_conv_fwd":
         B, N, k, S, C = a[:5]
@@ -247,16 +256,25 @@ def _ncu_key(name, a):
     return None, None
 
 
-def dram_traffic(name, a):
+def dram_traffic(name, a, ms_per_launch=None):
     """dram__bytes_read.sum + dram__bytes_write.sum of the entry point's dominant kernel, per launch,
-    from the committed `ncu --set full` capture (profiles/kernel_traffic.json); None if not captured."""
-    prefix, grid = _ncu_key(name, a)
-    if prefix is None:
-        return None, None
+    from the committed `ncu --set full` capture (profiles/kernel_traffic.json); None if not captured.
+    The GEMM kernel serves every shape with the same grid: its launch is identified by duration (within 15 %)."""
     try:
         with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
             table = json.load(f)
     except Exception:
+        return None, None
+    if name == "hsp_gemm_bf16" and ms_per_launch:
+        best = None
+        for e in table:
+            if e["kernel"].startswith("gemm::gemm_tc_kernel") and e.get("duration_us"):
+                d = abs(e["duration_us"] - ms_per_launch * 1e3) / (ms_per_launch * 1e3)
+                if d <= 0.15 and (best is None or d < best[0]):
+                    best = (d, e)
+        return (best[1]["dram_bytes"], best[1].get("source")) if best else (None, None)
+    prefix, grid = _ncu_key(name, a)
+    if prefix is None:
         return None, None
     for e in table:
         if e["kernel"].startswith(prefix) and (grid is None or e["grid"] == grid):
@@ -269,8 +287,10 @@ LIMITER = {
     "hsp_gemm_bf16": "tcgen05 tensor pipe at the power-capped clock; TMA tensor loads L2 -> shared (5-stage ring), "
                      "epilogue (tcgen05.ld -> bf16 -> TMA store + BatchNorm partials) overlapped via 2 TMEM buffers",
     "hsp_graph_conv_bwd": "L2 atomic (RED.f32) throughput: N*S*C scattered adds per object; DRAM 16-19 %, issue 16-18 %",
+    "hsp_graph_conv_bwd_obj": "winner byte -> pair record -> support value latency chain (35 % of stall samples) + shared-memory "
+                              "atomics (23 %); slab written once, no memset / RED / cast pass",
     "hsp_graph_conv_fwd": "instruction issue (N*k*S*C element ops from L2-resident rows); DRAM 7 %, issue 68 %",
-    "hsp_knn_feat": "tcgen05 filter epilogue + exact-refine L2 gathers; DRAM 2 %, tensor pipe 14 %",
+    "hsp_knn_feat": "L2 -> SM streaming of the candidate tiles (two sweeps) in the tcgen05 filter + exact-refine L2 row gathers",
     "hsp_knn3": "ALU pipe (selection network); DRAM 0 %",
     "hsp_surface_conv_fwd": "ALU/FMA issue; DRAM 3 %",
     "hsp_bn_relu_bwd": "HBM stream (5 passes over the activation matrix), 75 % of measured copy bandwidth at 1024 channels",
@@ -515,7 +535,7 @@ def run_b200(args):
     fp32_tf = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12      # 148 SMs x 128 FMA lanes x 2 flops at the SAMPLED clock
     top = rows[0]
     own_ms = sum(r["ms_per_step"] for r in rows)
-    traffic, traffic_src = dram_traffic(top["kernel"], tuple(top["dims"]))
+    traffic, traffic_src = dram_traffic(top["kernel"], tuple(top["dims"]), top.get("ms_per_launch"))
     if top["kernel"] == "hsp_gemm_bf16":     # a tensor-core kernel: its yardstick is the measured bf16 GEMM rate
         ach = top["alg_flops"] / (top["ms_per_launch"] * 1e-3) / 1e12
         bound, unit, pk = "tensor", "TFLOP/s", peak_tf
