@@ -104,16 +104,30 @@ class TrainStep:
 
     # ---- early gradient bucket: all-reduce on a side stream as soon as the last head gradient has landed
     def _on_early_grad(self, p):
-        # runs on an autograd worker thread, whose "current stream" is not the step's: fork from the stream
-        # the step itself runs on (recorded by _body; the capture stream in graph mode)
+        # runs on an autograd worker thread, whose "current stream" is not the step's: work on / fork from the
+        # stream the step itself runs on (recorded by _body; the capture stream in graph mode)
         self._pending -= 1
         if self._pending == 0:
+            n = len(self.flat.early_params)
+            with torch.cuda.stream(self._main):
+                self._gather(0, n)                # the heads' gradients -> their slice of the flat buffer
             if self._side is None:
                 self._side = torch.cuda.Stream(device=p.device)
             self._side.wait_stream(self._main)
             with torch.cuda.stream(self._side):
                 self.flat.all_reduce_early()
             self._early_done = True
+
+    def _gather(self, lo, hi):
+        """Autograd handed over one gradient tensor per parameter (`.grad` was None): copy those of parameters
+        lo..hi into the flat buffer with ONE multi-tensor copy (no per-parameter `grad += g` launch, ~160 of
+        them) and point `.grad` back at the flat views."""
+        ps, vs = self.flat.params[lo:hi], self._views[lo:hi]
+        got = [(v, p.grad) for v, p in zip(vs, ps) if p.grad is not None]
+        if got:
+            torch._foreach_copy_([v for v, _ in got], [g for _, g in got])
+        for v, p in zip(vs, ps):
+            p.grad = v
 
     # ---- the step itself
     def _body(self, batch, draw_inline):
@@ -128,20 +142,12 @@ class TrainStep:
             if total is None:
                 total = sum(v.reshape(()).float() for grp in losses.values() for v in grp.values())
             self.flat.zero()
-            if self._overlap:
-                total.backward()                  # gradients accumulate into the flat views as they arrive
-            else:
-                # one rank: let autograd hand over each gradient tensor (no per-parameter `grad += g` launch,
-                # ~160 of them) and gather them into the flat buffer with one multi-tensor copy
-                views = [p.grad for p in self.flat.params]
-                for p in self.flat.params:
-                    p.grad = None
-                total.backward()
-                got = [(v, p.grad) for v, p in zip(views, self.flat.params) if p.grad is not None]
-                if got:
-                    torch._foreach_copy_([v for v, _ in got], [g for _, g in got])
-                for v, p in zip(views, self.flat.params):
-                    p.grad = v
+            self._views = [p.grad for p in self.flat.params]
+            for p in self.flat.params:
+                p.grad = None
+            total.backward()
+            n_early = len(self.flat.early_params) if (self._overlap and self._early_done) else 0
+            self._gather(n_early, len(self.flat.params))
         finally:
             gcn3d.set_pool_rows_provider(prev)
         if self._overlap and self._early_done:
