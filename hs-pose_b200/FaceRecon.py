@@ -46,7 +46,7 @@ def bn_points(bn: nn.BatchNorm1d, x_bnc, relu=False):
 def conv1x1(conv: nn.Conv1d, x_bnc, pad_in=0, pad_out=0):
     """nn.Conv1d(kernel_size=1) applied in (bs, N, C) layout.  pad_in / pad_out append
     zero input columns / output rows to the weight so GEMM dims stay 16-byte aligned."""
-    w, b = conv.weight[:, :, 0], conv.bias
+    w, b = conv.weight.squeeze(-1), conv.bias
     if mixed_precision() and x_bnc.is_cuda:
         # K6 tensor-core GEMM (forward, dgrad, wgrad); the kernel pads / clips ragged widths itself
         if pad_in:
@@ -70,7 +70,7 @@ def _eval_folded(conv: nn.Conv1d, bn: nn.BatchNorm1d, x_bnc, relu):
     if cache is None or cache[0] != key:
         with torch.no_grad():
             s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
-            w = conv.weight[:, :, 0] * s[:, None]
+            w = conv.weight.squeeze(-1) * s[:, None]
             pad_in = x_bnc.shape[-1] - conv.in_channels
             if pad_in:
                 w = F.pad(w, (0, pad_in))
@@ -92,7 +92,7 @@ def conv_bn_relu_points(conv: nn.Conv1d, bn: nn.BatchNorm1d, x_bnc, relu=True):
     pad_in = shape[-1] - conv.in_channels
     if (bn.training and mixed_precision() and x_bnc.is_cuda and conv.out_channels % 8 == 0
             and shape[-1] % 8 == 0 and x_bnc.numel() // shape[-1] > 1):
-        w = conv.weight[:, :, 0]
+        w = conv.weight.squeeze(-1)
         if pad_in:
             w = F.pad(w, (0, pad_in))
         ops.bump_counter(bn.num_batches_tracked)
@@ -120,7 +120,7 @@ def multi_conv_bn_relu_points(pairs, x_bnc):
         return [conv_bn_relu_points(c, b, x_bnc) for c, b in pairs]
     blocks = []
     for conv, bn in pairs:
-        w = conv.weight[:, :, 0]
+        w = conv.weight.squeeze(-1)
         pad_in = shape[-1] - conv.in_channels
         if pad_in:
             w = F.pad(w, (0, pad_in))
@@ -266,7 +266,7 @@ class FaceRecon(nn.Module):
             x = torch.cat([f_global.unsqueeze(1).expand(-1, n, -1), conv1d_out, vertices], dim=2)
             return seq_points(self.face_head, x)
         conv0 = self.face_head[0]
-        w = conv0.weight[:, :, 0]
+        w = conv0.weight.squeeze(-1)
         cg = f_global.shape[1]
         per_obj = ops.linear_tc(f_global, w[:, :cg], conv0.bias).float()         # (bs, 512)
         pad = (-(conv1d_out.shape[2] + 3)) % 8

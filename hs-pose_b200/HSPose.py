@@ -17,6 +17,7 @@ import torch.nn as nn
 
 from . import augment, ops
 from .PoseNet9D import PoseNet9D
+from .pc_sample import PC_sample
 from .flags import FLAGS
 from .losses import (chamfer_recon_loss, fs_net_loss, geo_transform_loss, get_gt_v, prop_rot_loss,
                      recon_6face_loss)
@@ -54,8 +55,18 @@ class HSPose(nn.Module):
                 do_loss=False):
         output_dict = {}
         if PC is None:
-            # reference HSPose.py:40-50 samples the cloud from `depth`; neither driver uses it
-            raise NotImplementedError("HSPose.forward needs PC (depth sampling is outside the hot path)")
+            # reference HSPose.py:40-50: the cloud is sampled from the depth ROI (K11, pc_sample.PC_sample)
+            if self.train_stage != 'PoseNet_only':
+                raise NotImplementedError
+            if depth is None or def_mask is None or camK is None or gt_2D is None:
+                raise ValueError("HSPose.forward needs PC, or depth + def_mask + camK + gt_2D to sample it from")
+            FLAGS.sample_method = 'basic'
+            # the reference draws (and never uses) a `sketch` tensor here; the draw is kept so that the CUDA
+            # generator is in the same state when data_augment consumes it
+            torch.rand([depth.shape[0], 6, depth.shape[2], depth.shape[3]], device=depth.device)
+            PC = PC_sample(def_mask, depth, camK, gt_2D)
+            if PC is None:
+                return output_dict, None
 
         PC = PC.detach()
         if FLAGS.train:

@@ -38,9 +38,9 @@ class _PointHead(nn.Module):
         else:
             x = torch.max(x, 1)[0]
         lin = ops.linear_tc if (mixed_precision() and x.is_cuda) else F.linear   # K6 on the mixed-precision path
-        x = F.relu(self.bn3(lin(x, self.conv3.weight[:, :, 0], self.conv3.bias)))
+        x = F.relu(self.bn3(lin(x, self.conv3.weight.squeeze(-1), self.conv3.bias)))
         x = self.drop1(x)
-        x = lin(x, self.conv4.weight[:, :, 0], self.conv4.bias)
+        x = lin(x, self.conv4.weight.squeeze(-1), self.conv4.bias)
         ops.flush_counters()
         return x.contiguous()
 

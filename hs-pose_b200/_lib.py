@@ -56,6 +56,10 @@ SIGNATURES = {
                                ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_int, c_int, P, P,
                                c_size_t, P]),
     "hsp_augment": (c_int, [P] * 15 + [ctypes.c_float] * 5 + [c_int] * 3 + [P] * 5),
+    "hsp_normalize_cols_fwd": (c_int, [P, c_int, ctypes.c_float, P, P, P]),
+    "hsp_normalize_cols_bwd": (c_int, [P, P, P, c_int, ctypes.c_float, P, P]),
+    "hsp_depth_to_cloud": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P]),
+    "hsp_sample_points": (c_int, [P, P, P, ctypes.c_ulonglong, c_int, c_int, c_int, P, P, P]),
     "hsp_split_bf16": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "hsp_residual_sum_fwd": (c_int, [P, P, c_int, P, P, c_int, P, P, c_int, c_int, c_int, P, P]),
     "hsp_residual_sum_bwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P]),

@@ -53,6 +53,62 @@ gather_max_bwd_kernel(const float* __restrict__ gout, const int32_t* __restrict_
   }
 }
 
+// Deterministic form of the same scatter (the default): warp = one SOURCE row j.  The object's (sampled row, slot)
+// -> source table (R x kuse ints) sits in shared memory; the warp scans it 32 entries at a time (ballot) and adds
+// the matching output gradients, where the saved arg-max names that slot, in ascending (r, slot) order.  Every
+// gfeat row is written exactly once: no float atomics, no zero-fill, bit-reproducible.
+constexpr int GMB_WARPS = 8;
+constexpr int GMB_MAXV = 4;                    // float4 accumulators per lane: C <= 512
+__global__ void __launch_bounds__(GMB_WARPS * 32)
+gather_max_bwd_det_kernel(const float* __restrict__ gout, const int32_t* __restrict__ idx,
+                          const int32_t* __restrict__ rows, const uint8_t* __restrict__ argmax, int N, int C,
+                          int R, int kuse, int kstride, float* __restrict__ gfeat) {
+  extern __shared__ int32_t s_tab[];           // [R * kuse]
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int T = R * kuse;
+  for (int t = threadIdx.x; t < T; t += GMB_WARPS * 32) {
+    const int r = t / kuse, sl = t - r * kuse;
+    const int i = rows ? __ldg(rows + r) : r;
+    s_tab[t] = __ldg(idx + ((size_t)b * N + i) * kstride + sl);
+  }
+  __syncthreads();
+  const int j = blockIdx.x * GMB_WARPS + warp;
+  if (j >= N) return;
+  const int c4 = C >> 2;
+  float4 acc[GMB_MAXV];
+#pragma unroll
+  for (int v = 0; v < GMB_MAXV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    unsigned m = __ballot_sync(0xffffffffu, t < T && s_tab[t] == j);
+    while (m) {
+      const int tt = t0 + __ffs(m) - 1;
+      m &= m - 1;
+      const int r = tt / kuse;
+      const uint32_t sl = (uint32_t)(tt - r * kuse);
+      const size_t o = ((size_t)b * R + r) * C;
+#pragma unroll
+      for (int v = 0; v < GMB_MAXV; ++v) {
+        const int q = lane + 32 * v;
+        if (q < c4) {
+          const uint32_t am = __ldg(reinterpret_cast<const uint32_t*>(argmax + o) + q);
+          const float4 g = __ldg(reinterpret_cast<const float4*>(gout + o) + q);
+          if ((am & 0xffu) == sl) acc[v].x += g.x;
+          if (((am >> 8) & 0xffu) == sl) acc[v].y += g.y;
+          if (((am >> 16) & 0xffu) == sl) acc[v].z += g.z;
+          if ((am >> 24) == sl) acc[v].w += g.w;
+        }
+      }
+    }
+  }
+  float4* dst = reinterpret_cast<float4*>(gfeat + ((size_t)b * N + j) * C);
+#pragma unroll
+  for (int v = 0; v < GMB_MAXV; ++v) {
+    const int q = lane + 32 * v;
+    if (q < c4) dst[q] = acc[v];
+  }
+}
+
 // Stage 1 of ORL: per-tile partial sums over points of max over neighbours.
 __global__ void __launch_bounds__(GO_THREADS)
 orl_partial_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx, int N, int C,
@@ -277,6 +333,55 @@ upsample_bwd_vec_kernel(const TO* __restrict__ gout, const int32_t* __restrict__
   }
 }
 
+// Deterministic form of the scatter-add (the default when nn != NULL): warp = one SOURCE row j.  The object's
+// nearest table (M ints) sits in shared memory; the warp scans it 32 targets at a time (ballot) and adds the rows
+// of the targets that map to j in ascending target order.  Every gfeat row is written exactly once (zeros when no
+// target maps to it): no float atomics, no zero-fill, bit-reproducible.
+constexpr int UBD_WARPS = 8;
+constexpr int UBD_ROWS = 2;                    // source rows per warp
+constexpr int UBD_MAXV = 4;                    // 8-channel vectors per lane: C <= 1024
+template <typename TO>
+__global__ void __launch_bounds__(UBD_WARPS * 32)
+upsample_bwd_det_kernel(const TO* __restrict__ gout, const int32_t* __restrict__ nn, int Nsrc, int M, int C,
+                        int ldo, int col0, float* __restrict__ gfeat) {
+  extern __shared__ int32_t s_nn[];            // [M]
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c8 = C >> 3;
+  for (int t = threadIdx.x; t < M; t += UBD_WARPS * 32) s_nn[t] = __ldg(nn + (size_t)b * M + t);
+  __syncthreads();
+  for (int rr = 0; rr < UBD_ROWS; ++rr) {
+    const int j = (blockIdx.x * UBD_WARPS + warp) * UBD_ROWS + rr;
+    if (j >= Nsrc) return;
+    float4 aa[UBD_MAXV], ab[UBD_MAXV];
+#pragma unroll
+    for (int v = 0; v < UBD_MAXV; ++v) aa[v] = ab[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t0 = 0; t0 < M; t0 += 32) {
+      const int t = t0 + lane;
+      unsigned m = __ballot_sync(0xffffffffu, t < M && s_nn[t] == j);
+      while (m) {
+        const int i = t0 + __ffs(m) - 1;
+        m &= m - 1;
+        const TO* src = gout + ((size_t)b * M + i) * ldo + col0;
+#pragma unroll
+        for (int v = 0; v < UBD_MAXV; ++v) {
+          const int q = lane + 32 * v;
+          if (q < c8) {
+            float4 a, c;
+            Out8<TO>::load(src + 8 * q, a, c);
+            aa[v].x += a.x; aa[v].y += a.y; aa[v].z += a.z; aa[v].w += a.w;
+            ab[v].x += c.x; ab[v].y += c.y; ab[v].z += c.z; ab[v].w += c.w;
+          }
+        }
+      }
+    }
+    float* dst = gfeat + ((size_t)b * Nsrc + j) * C;
+#pragma unroll
+    for (int v = 0; v < UBD_MAXV; ++v) {
+      const int q = lane + 32 * v;
+      if (q < c8) Out8<float>::store(dst + 8 * q, aa[v], ab[v]);
+    }
+  }
+}
+
 static bool vec8_ok(const void* a, const void* b, int C, int ldo, int col0, int esz) {
   return (C % 8) == 0 && ((size_t)ldo * esz) % 16 == 0 && ((size_t)col0 * esz) % 16 == 0 &&
          ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0;
@@ -351,10 +456,21 @@ extern "C" int hsp_gather_max_bwd(const float* gout, const int32_t* idx, const i
   if (!gout || !idx || !argmax || !gfeat || B < 0 || N <= 0 || C <= 0 || R < 0 || kuse <= 0 ||
       kuse > kstride || B > 65535 || (!rows && R != N))
     return HSP_EINVAL;
-  if (B == 0 || R == 0) return HSP_OK;
+  if (B == 0) return HSP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t tab = (size_t)R * kuse * sizeof(int32_t);
+  if (R > 0 && (C % 4) == 0 && C <= 128 * GMB_MAXV && tab <= 48 * 1024 && ((uintptr_t)gout % 16) == 0 &&
+      ((uintptr_t)gfeat % 16) == 0 && ((uintptr_t)argmax % 4) == 0) {
+    gather_max_bwd_det_kernel<<<dim3((N + GMB_WARPS - 1) / GMB_WARPS, B), GMB_WARPS * 32, tab, st>>>(
+        gout, idx, rows, argmax, N, C, R, kuse, kstride, gfeat);
+    HSP_LAUNCH_CHECK();
+    return HSP_OK;
+  }
+  // other shapes: float atomics into a zeroed buffer (order-dependent in the last bit)
+  if (cudaMemsetAsync(gfeat, 0, (size_t)B * N * C * sizeof(float), st) != cudaSuccess) return HSP_ELAUNCH;
+  if (R == 0) return HSP_OK;
   dim3 grid((R + GO_PT - 1) / GO_PT, B, (C + GO_THREADS - 1) / GO_THREADS);
-  gather_max_bwd_kernel<<<grid, GO_THREADS, 0, (cudaStream_t)stream>>>(
-      gout, idx, rows, argmax, N, C, R, kstride, gfeat);
+  gather_max_bwd_kernel<<<grid, GO_THREADS, 0, st>>>(gout, idx, rows, argmax, N, C, R, kstride, gfeat);
   HSP_LAUNCH_CHECK();
   return HSP_OK;
 }
@@ -455,8 +571,26 @@ extern "C" int hsp_upsample_rows_bwd(const void* gout, const int32_t* nn, int B,
     return HSP_EINVAL;
   if (!nn && Nsrc != M) return HSP_EINVAL;
   if (gout_dtype != HSP_DTYPE_F32 && gout_dtype != HSP_DTYPE_BF16) return HSP_EINVAL;
-  if (B == 0 || M == 0) return HSP_OK;
-  if (vec8_ok(gout, gfeat, C, ldo, col0, gout_dtype == HSP_DTYPE_BF16 ? 2 : 4)) {
+  if (B == 0) return HSP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = vec8_ok(gout, gfeat, C, ldo, col0, gout_dtype == HSP_DTYPE_BF16 ? 2 : 4);
+  if (nn && M > 0 && vec && C <= 256 * UBD_MAXV && (size_t)M * sizeof(int32_t) <= 48 * 1024) {
+    // scatter-add as a gather over the source rows: deterministic, writes every gfeat row once
+    dim3 gd((Nsrc + UBD_WARPS * UBD_ROWS - 1) / (UBD_WARPS * UBD_ROWS), B);
+    const size_t sm = (size_t)M * sizeof(int32_t);
+    if (gout_dtype == HSP_DTYPE_BF16)
+      upsample_bwd_det_kernel<__nv_bfloat16><<<gd, UBD_WARPS * 32, sm, st>>>((const __nv_bfloat16*)gout, nn, Nsrc, M, C,
+                                                                         ldo, col0, gfeat);
+    else
+      upsample_bwd_det_kernel<float><<<gd, UBD_WARPS * 32, sm, st>>>((const float*)gout, nn, Nsrc, M, C, ldo, col0,
+                                                                 gfeat);
+    HSP_LAUNCH_CHECK();
+    return HSP_OK;
+  }
+  // the float-atomics scatter accumulates: it starts from zeros (the identity copy overwrites everything)
+  if (nn && cudaMemsetAsync(gfeat, 0, (size_t)B * Nsrc * C * sizeof(float), st) != cudaSuccess) return HSP_ELAUNCH;
+  if (M == 0) return HSP_OK;
+  if (vec) {
     dim3 gv((M * (C / 8) + 255) / 256, B);
     if (gout_dtype == HSP_DTYPE_BF16)
       upsample_bwd_vec_kernel<__nv_bfloat16><<<gv, 256, 0, (cudaStream_t)stream>>>(

@@ -11,11 +11,13 @@ one graph launch.  Hand-written kernels enter the graph like any other launch (t
 """
 import contextlib
 import copy
+import os
 
 import torch
 
 from . import gcn3d, geom, ops, optim, parallel
 
+_WEIGHT_SHADOW = os.environ.get("HSP_WEIGHT_SHADOW", "1") != "0"   # A/B switch for the bf16 parameter shadow
 _RING = 4   # pinned staging slots per Pool_layer permutation (bounds how far the CPU may run ahead)
 
 
@@ -136,7 +138,10 @@ class TrainStep:
         self._main = torch.cuda.current_stream()
         prev = gcn3d.set_pool_rows_provider(self._provider)
         try:
-            with self._tf32_scope(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+            # mixed precision: ONE bf16 cast of the flat parameter buffer per step; the GEMMs read views of it
+            shadow = self.flat.refresh_shadow() if (self.amp and _WEIGHT_SHADOW) else None
+            with self._tf32_scope(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp), \
+                    ops.weight_shadow(self.flat.flat_param, shadow):
                 _, losses = self.model(**batch, do_loss=True)
             total = getattr(losses, "total", None)      # HSPose's fused loss path sums its terms in one reduction
             if total is None:

@@ -150,10 +150,11 @@ def _orl_fuse(feature, vertices, neighbor_num, conv2_weight, f_STE=None, ste_xyz
     layer's `+ f_STE` (gcn3d.py:90 / :156) folded into the same pass (K5d) when given."""
     C = feature.shape[2]
     G = ops.orl_global(feature, _geo_index32_exact(vertices, neighbor_num))  # (B,C)
-    W2 = conv2_weight[:, :, 0]
+    W2 = conv2_weight.squeeze(-1)
     if torch.is_autocast_enabled("cuda") and feature.is_cuda and C % 8 == 0:
-        lin = ops.linear_tc(feature, W2[:, :C])                              # K6 (bf16 operands, fp32 accumulate)
-        gproj = ops.linear_tc(G, W2[:, C:]).float()                          # (B,C)
+        W2f, W2g = ops.split_halves(W2, C)                                   # one cat in the backward
+        lin = ops.linear_tc(feature, W2f)                                    # K6 (bf16 operands, fp32 accumulate)
+        gproj = ops.linear_tc(G, W2g).float()                                # (B,C)
     else:
         lin = F.linear(feature, W2[:, :C])
         with torch.autocast("cuda", enabled=False):
@@ -167,6 +168,14 @@ def _orl_fuse(feature, vertices, neighbor_num, conv2_weight, f_STE=None, ste_xyz
             f_STE = F.linear(vertices.float(), ste_xyz_weight.float())
     out = feature + lin + gproj.unsqueeze(1)
     return out if f_STE is None else out + f_STE
+
+
+def _unit_dirs(directions):
+    """F.normalize(directions, dim=0) (reference gcn3d.py:95, :162); one launch each way on the mixed-precision
+    train path, the PyTorch composite (bit-for-bit the reference's) on the fp32 parity path."""
+    if directions.is_cuda and torch.is_autocast_enabled("cuda"):
+        return ops.normalize_dirs(directions)
+    return F.normalize(directions, dim=0)
 
 
 # -------------------------------------------------------------------- layers
@@ -193,13 +202,13 @@ class HSlayer_surface(nn.Module):
         # STE (Conv1d 3 -> C on the coordinates, gcn3d.py:86) is folded into the fused residual pass
         feature = self.graph_conv(None, vertices, neighbor_num)
         return _orl_fuse(feature, vertices, neighbor_num, self.conv2.weight,
-                         ste_xyz_weight=self.STE_layer.weight[:, :, 0])
+                         ste_xyz_weight=self.STE_layer.weight.squeeze(-1))
 
     def graph_conv(self, receptive_fields_norm, vertices, neighbor_num):
         """K3.  `receptive_fields_norm` is accepted for signature parity and ignored:
         the unit directions are recomputed in-kernel from the RF-P neighbour table."""
         idx32 = _geo_index32_exact(vertices, neighbor_num)
-        dirn = F.normalize(self.directions, dim=0)
+        dirn = _unit_dirs(self.directions)
         return ops.surface_conv(vertices, idx32, dirn, self.support_num, self.kernel_num)
 
     def ORL_forward(self, feature, vertices, neighbor_num):
@@ -232,9 +241,9 @@ class HS_layer(nn.Module):
 
     def forward(self, vertices, feature_map, neighbor_num):
         if torch.is_autocast_enabled("cuda") and feature_map.is_cuda and self.in_channel % 8 == 0:
-            f_STE = ops.linear_tc(feature_map, self.STE_layer.weight[:, :, 0])    # K6
+            f_STE = ops.linear_tc(feature_map, self.STE_layer.weight.squeeze(-1))    # K6
         else:
-            f_STE = F.linear(feature_map, self.STE_layer.weight[:, :, 0])
+            f_STE = F.linear(feature_map, self.STE_layer.weight.squeeze(-1))
         neighbor_index = _feature_index32(feature_map, neighbor_num)          # RF-F (K2)
         feature = self.graph_conv(None, neighbor_index, feature_map, vertices, neighbor_num)
         return _orl_fuse(feature, vertices, neighbor_num, self.conv2.weight, f_STE)
@@ -247,7 +256,7 @@ class HS_layer(nn.Module):
         idx32 = neighbor_index if neighbor_index.dtype == torch.int32 else neighbor_index.to(torch.int32)
         if torch.is_autocast_enabled("cuda"):
             # mixed precision: bf16 P straight from the tensor-core GEMM into the gather kernel
-            return ops.hs_conv_mixed(vertices, idx32, F.normalize(self.directions, dim=0), feature_map,
+            return ops.hs_conv_mixed(vertices, idx32, _unit_dirs(self.directions), feature_map,
                                      self.weights, self.bias, self.support_num, self.out_channel)
         P = torch.addmm(self.bias, feature_map.reshape(-1, self.in_channel), self.weights)
         P = P.view(feature_map.shape[0], feature_map.shape[1], -1)

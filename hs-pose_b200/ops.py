@@ -4,6 +4,7 @@ PyTorch is plumbing here: it owns device memory and the stream; every op below
 is one or two launches of a hand-written sm_100a kernel in libhspose_b200.so.
 No op has a PyTorch/CPU fallback — a missing library or a CPU tensor raises.
 """
+import contextlib
 import ctypes
 import os
 
@@ -139,6 +140,59 @@ def direction_norm(xyz, idx32, return_unnormed=False):
 
 
 # ------------------------------------------------------------ graph convs
+class _NormalizeCols(torch.autograd.Function):
+    """F.normalize(d, dim=0) for the (3, S*C) support directions, one launch each way."""
+
+    @staticmethod
+    def forward(ctx, d):
+        d = _need(d, torch.float32, "directions")
+        n = d.shape[1]
+        with torch.cuda.device(d.device):
+            out, nrm = torch.empty_like(d), torch.empty(n, dtype=torch.float32, device=d.device)
+            _call("hsp_normalize_cols_fwd", _p(d), n, ctypes.c_float(1e-12), _p(out), _p(nrm), _stream())
+        ctx.save_for_backward(out, nrm)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out, nrm = ctx.saved_tensors
+        g = _need(g, torch.float32, "g")
+        with torch.cuda.device(g.device):
+            gd = torch.empty_like(out)
+            _call("hsp_normalize_cols_bwd", _p(g), _p(out), _p(nrm), out.shape[1], ctypes.c_float(1e-12), _p(gd),
+                  _stream())
+        return gd
+
+
+def normalize_dirs(d):
+    """Unit support directions (reference gcn3d.py:95, :162: F.normalize(self.directions, dim=0))."""
+    if d.dim() != 2 or d.shape[0] != 3:
+        raise ValueError("normalize_dirs expects the (3, S*C) direction parameter")
+    return _NormalizeCols.apply(d)
+
+
+class _SplitHalves(torch.autograd.Function):
+    """(W[:, :h], W[:, h:]) of the ORL 1x1 convolution weight (C, 2C); the gradient is ONE concatenation instead of
+    two zero-filled (C, 2C) buffers, two slice copies and an add."""
+
+    @staticmethod
+    def forward(ctx, W, h):
+        ctx.h, ctx.shape = h, W.shape
+        return W[:, :h], W[:, h:]
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        if ga is None:
+            ga = gb.new_zeros(ctx.shape[0], ctx.h)
+        if gb is None:
+            gb = ga.new_zeros(ctx.shape[0], ctx.shape[1] - ctx.h)
+        return torch.cat([ga, gb], dim=1), None
+
+
+def split_halves(W, h):
+    return _SplitHalves.apply(W, h)
+
+
 class _SurfaceConv(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
@@ -262,7 +316,7 @@ class _HSConvMixed(torch.autograd.Function):
         fm = _need(fm, torch.float32, "feature_map")
         B, N, Cin = fm.shape
         fm16 = fm.reshape(B * N, Cin).to(torch.bfloat16)
-        W16 = W.to(torch.bfloat16)                       # (Cin, (S+1)C): read MN-major as the B operand
+        W16 = _as_gemm_operand(W)                        # (Cin, (S+1)C): read MN-major as the B operand
         P = gemm_bf16(fm16, W16, b_mn=True, bias=bias).view(B, N, (S + 1) * C)
         need_grad = any(ctx.needs_input_grad)
         out, am = _graph_conv_fwd_raw(xyz, idx32, dirn, P, S, C, need_grad)
@@ -282,7 +336,9 @@ class _HSConvMixed(torch.autograd.Function):
         gP16, gdirn, gb = _graph_conv_bwd_raw(xyz, idx32, dirn, P, am, gout, S, C, want_gbias=True,
                                               gp_dtype=torch.bfloat16)
         gP16 = gP16.view(B * N, (S + 1) * C)
-        gfm = gemm_bf16(gP16, W16).view(B, N, Cin).float() if ctx.needs_input_grad[3] else None
+        # the input gradient leaves the GEMM epilogue in fp32 (feature maps are fp32: no bf16 round trip + cast pass)
+        gfm = (gemm_bf16(gP16, W16, out_dtype=torch.float32).view(B, N, Cin)
+               if ctx.needs_input_grad[3] else None)
         gW = gemm_bf16(fm16, gP16, a_mn=True, b_mn=True, out_dtype=torch.float32,
                        splits=gemm_splits(Cin, (S + 1) * C, B * N))
         return None, None, gdirn, gfm, gW, gb, None, None
@@ -322,7 +378,7 @@ class _GatherMax(torch.autograd.Function):
         B, N, C, R, kuse, kstride = ctx.dims
         gout = _need(gout.float(), torch.float32, "gout")
         with torch.cuda.device(gout.device):
-            gfeat = torch.zeros(B, N, C, dtype=torch.float32, device=gout.device)
+            gfeat = torch.empty(B, N, C, dtype=torch.float32, device=gout.device)   # written in full by the call
             _call("hsp_gather_max_bwd", _p(gout), _p(idx32), _p(rows32), _p(am), B, N, C, R,
                   kuse, kstride, _p(gfeat), _stream())
         return gfeat, None, None, None
@@ -395,7 +451,7 @@ class _GatherRows(torch.autograd.Function):
         B, Nsrc, M, C = ctx.dims
         gout = _need(gout.float(), torch.float32, "gout")
         with torch.cuda.device(gout.device):
-            gfeat = torch.zeros(B, Nsrc, C, dtype=torch.float32, device=gout.device)
+            gfeat = torch.empty(B, Nsrc, C, dtype=torch.float32, device=gout.device)   # written in full by the call
             _call("hsp_upsample_rows_bwd", _p(gout), _p(nn32), B, Nsrc, M, C, C, 0, F32, _p(gfeat),
                   _stream())
         return gfeat, None
@@ -460,10 +516,7 @@ class _ConcatUpsample(torch.autograd.Function):
                 elif bcast[i]:
                     grads.append(gout[:, :, col:col + w].sum(dim=1, dtype=torch.float32))
                 else:
-                    if nn is not None:
-                        g = torch.zeros(B, nsrcs[i], w, dtype=torch.float32, device=gout.device)
-                    else:
-                        g = torch.empty(B, M, w, dtype=torch.float32, device=gout.device)
+                    g = torch.empty(B, nsrcs[i] if nn is not None else M, w, dtype=torch.float32, device=gout.device)
                     _call("hsp_upsample_rows_bwd", _p(gout), _p(nn), B, nsrcs[i], M, w, ld, col, dt,
                           _p(g), _stream())
                     grads.append(g)
@@ -672,13 +725,14 @@ class _LinearBnRelu(torch.autograd.Function):
         ctx.save_for_backward(xb, Wb, y, g32, b32, stats)
         ctx.relu, ctx.has_bias = int(relu), b is not None
         ctx.rpg = rows_per_group if bias_rows is not None else 0
+        ctx.dx_dtype = _dx_dtype(x)
         return z
 
     @staticmethod
     def backward(ctx, dz):
         xb, Wb, y, g32, b32, stats = ctx.saved_tensors
         dy, dgamma, dbeta, colsum = _bn_bwd_raw(y, dz, g32, b32, stats, ctx.relu, ctx.has_bias)
-        dx = gemm_bf16(dy, Wb, b_mn=True) if ctx.needs_input_grad[0] else None
+        dx = gemm_bf16(dy, Wb, b_mn=True, out_dtype=ctx.dx_dtype) if ctx.needs_input_grad[0] else None
         dW = _wgrad(dy, xb)
         drows = None
         if ctx.rpg:      # d bias_rows[g] = sum of dY over the group's rows
@@ -731,6 +785,7 @@ class _MultiLinearBnRelu(torch.autograd.Function):
             off += widths[i]
         ctx.save_for_backward(*saved)
         ctx.meta = meta
+        ctx.dx_dtype = _dx_dtype(x)
         return tuple(outs)
 
     @staticmethod
@@ -750,7 +805,7 @@ class _MultiLinearBnRelu(torch.autograd.Function):
             _, dgamma, dbeta, colsum = _bn_bwd_raw(ycat[:, off:off + wd], dz, g32, b32, stats, relu, has_bias,
                                                    dx_out=dycat[:, off:off + wd])
             grads.append((colsum, dgamma, dbeta))
-        dx = gemm_bf16(dycat, Wcat, b_mn=True) if ctx.needs_input_grad[0] else None
+        dx = gemm_bf16(dycat, Wcat, b_mn=True, out_dtype=ctx.dx_dtype) if ctx.needs_input_grad[0] else None
         dWcat = _wgrad(dycat, xb)                                            # (tot, K) fp32
         out = []
         for (relu, has_bias, off, wd), (colsum, dgamma, dbeta) in zip(ctx.meta, grads):
@@ -815,8 +870,28 @@ def gemm_bf16(a, b, a_mn=False, b_mn=False, bias=None, out=None, out_dtype=torch
     return (res, st) if stats else res
 
 
+_shadow = None     # (base pointer, bytes, device, bf16 buffer) of the flat fp32 parameter buffer, inside a step
+
+
+@contextlib.contextmanager
+def weight_shadow(flat_fp32, flat_bf16):
+    """Within the block, an fp32 GEMM operand that is a view of `flat_fp32` (the engine's flat parameter buffer)
+    is served as the same view of `flat_bf16` (its bf16 copy, refreshed by the caller) instead of a cast."""
+    global _shadow
+    prev = _shadow
+    _shadow = (flat_fp32.data_ptr(), flat_fp32.numel() * 4, flat_fp32.device, flat_bf16) if flat_bf16 is not None else None
+    try:
+        yield
+    finally:
+        _shadow = prev
+
+
 def _as_gemm_operand(t):
     """bf16 2-D matrix whose row pitch is 16-byte aligned (TMA requirement); pads columns if needed."""
+    if t.dtype == torch.float32 and _shadow is not None and t.device == _shadow[2]:
+        off = t.data_ptr() - _shadow[0]
+        if 0 <= off < _shadow[1]:
+            t = _shadow[3].as_strided(t.shape, t.stride(), off // 4)
     if t.dtype != torch.bfloat16:
         t = t.to(torch.bfloat16)
     if t.stride(-1) != 1 or (t.stride(0) * 2) % 16 != 0 or t.data_ptr() % 16 != 0:
@@ -825,6 +900,12 @@ def _as_gemm_operand(t):
         buf[:, :cols] = t
         t = buf[:, :cols]
     return t
+
+
+def _dx_dtype(x):
+    """dtype the input gradient of a tensor-core Linear leaves the GEMM epilogue in: the input's own (fp32 feature
+    maps get an fp32 gradient directly — autograd would otherwise cast the bf16 result in a separate pass)."""
+    return torch.float32 if x.dtype == torch.float32 else torch.bfloat16
 
 
 def _wgrad(dy, x):
@@ -844,13 +925,14 @@ class _LinearTC(torch.autograd.Function):
         y = gemm_bf16(xb, Wb, bias=b)
         ctx.save_for_backward(xb, Wb)
         ctx.has_bias = b is not None
+        ctx.dx_dtype = _dx_dtype(x)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         xb, Wb = ctx.saved_tensors
         dyb = _as_gemm_operand(dy)
-        dx = gemm_bf16(dyb, Wb, b_mn=True) if ctx.needs_input_grad[0] else None
+        dx = gemm_bf16(dyb, Wb, b_mn=True, out_dtype=ctx.dx_dtype) if ctx.needs_input_grad[0] else None
         dW = _wgrad(dyb, xb) if ctx.needs_input_grad[1] else None
         db = dyb.sum(dim=0, dtype=torch.float32) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return dx, dW, db
@@ -970,6 +1052,50 @@ def augment(PC, R, t, s, mean_shape, sym, aug_bb, aug_rt_t, aug_rt_r, model_poin
         _call("hsp_augment", *[_p(a) for a in args], f(probs[0]), f(probs[1]), f(probs[2]), f(probs[3]), f(pc_r),
               B, N, model_point.shape[1], _p(PC_o), _p(R_o), _p(t_o), _p(s_o), _stream())
     return PC_o, R_o, t_o, s_o
+
+
+# ------------------------------------------------------------ K11: input pre-stage (depth ROI -> sampled cloud)
+def depth_to_cloud(depth, mask, xymap, camK):
+    """Back-projection + order-preserving compaction of the valid pixels (K11).
+    depth, mask (B,H,W) or (B,1,H,W); xymap (B,2,H,W); camK (B,3,3) — float64 selects the numpy (float64)
+    arithmetic of datasets/load_data.py:322-333, float32 the torch arithmetic of pc_sample.py:24-54.
+    -> cloud (B, H*W, 3) fp32 metres (rows >= count[b] unspecified), count (B,) int32."""
+    if depth.dim() == 4:
+        depth = depth[:, 0]
+    if mask.dim() == 4:
+        mask = mask[:, 0]
+    depth = _need(depth.float(), torch.float32, "depth")
+    mask = _need(mask.float(), torch.float32, "mask")
+    xymap = _need(xymap.float(), torch.float32, "xymap")
+    B, H, W = depth.shape
+    if mask.shape != (B, H, W) or xymap.shape != (B, 2, H, W) or camK.shape != (B, 3, 3):
+        raise ValueError("depth_to_cloud: depth/mask (B,H,W), xymap (B,2,H,W), camK (B,3,3)")
+    f64 = camK.dtype == torch.float64
+    camK = _need(camK, torch.float64 if f64 else torch.float32, "camK")
+    with torch.cuda.device(depth.device):
+        cloud = torch.empty(B, H * W, 3, dtype=torch.float32, device=depth.device)
+        count = torch.empty(B, dtype=torch.int32, device=depth.device)
+        _call("hsp_depth_to_cloud", _p(depth), _p(mask), _p(xymap), _p(camK), int(f64), B, H, W, _p(cloud),
+              _p(count), _stream())
+    return cloud, count
+
+
+def sample_points(cloud, count, n_pts, choose=None, seed=0, status=None):
+    """n_pts points per object from the compacted cloud (K11).  choose (B,n_pts) int: the caller's draw
+    (gather); None: the device rule — tile when count <= n_pts (load_data.py:316-317), else a random subset
+    without replacement keyed by `seed`.  status: optional int32 device scalar (see the header)."""
+    cloud = _need(cloud, torch.float32, "cloud")
+    count = _need(count, torch.int32, "count")
+    B, cap, _ = cloud.shape
+    if choose is not None:
+        choose = _need(choose.to(torch.int32), torch.int32, "choose")
+        if choose.shape != (B, n_pts):
+            raise ValueError("sample_points: choose must be (B, n_pts)")
+    with torch.cuda.device(cloud.device):
+        out = torch.empty(B, n_pts, 3, dtype=torch.float32, device=cloud.device)
+        _call("hsp_sample_points", _p(cloud), _p(count), _p(choose), ctypes.c_ulonglong(int(seed) & (2 ** 64 - 1)),
+              B, cap, int(n_pts), _p(out), _p(status), _stream())
+    return out
 
 
 # ------------------------------------------------------------ fp32-accurate GEMM on the bf16 tensor cores

@@ -72,12 +72,13 @@ class FlatGradients:
             self.params = first + rest
             self.n_early = sum(p.numel() for p in first)
             self.early_params = first
-        # every parameter starts on a 16-byte boundary of the flat buffers (kernels read weights and write
-        # gradients with vector accesses); the few padding elements stay zero
+        # every parameter starts on a 32-byte boundary of the flat fp32 buffers (kernels read weights and write
+        # gradients with vector accesses) = a 16-byte boundary of the bf16 shadow of the parameters, which TMA
+        # descriptors need; the few padding elements stay zero
         self.offsets, off = [], 0
         for p in self.params:
             self.offsets.append(off)
-            off += (p.numel() + 3) // 4 * 4
+            off += (p.numel() + 7) // 8 * 8
         n = off
         if self.n_early:
             self.n_early = self.offsets[len(self.early_params)] if len(self.early_params) < len(self.params) else n
@@ -104,6 +105,17 @@ class FlatGradients:
             self.flat_param = torch.nn.Parameter(flat)
             self.flat_param.grad = self.flat
         return self.flat_param
+
+    def refresh_shadow(self):
+        """bf16 copy of ALL parameters in one launch (needs flatten_params()): the tensor-core GEMMs of the
+        mixed-precision step read their weights as views of this buffer (ops.weight_shadow) instead of casting
+        ~40 weight tensors one by one every step."""
+        if self.flat_param is None:
+            return None
+        if getattr(self, "shadow16", None) is None:
+            self.shadow16 = torch.empty_like(self.flat_param.data, dtype=torch.bfloat16)
+        self.shadow16.copy_(self.flat_param.data)
+        return self.shadow16
 
     def zero(self):
         """zero_grad() that keeps the views (never set_to_none)."""

@@ -145,8 +145,9 @@ int hsp_graph_conv_bwd_obj(const float* xyz, const int32_t* idx, const float* di
 int hsp_gather_max_fwd(const float* feat, const int32_t* idx, const int32_t* rows,
                        int B, int N, int C, int R, int kuse, int kstride,
                        float* out, uint8_t* argmax, void* stream);
-/* gfeat (B,N,C) += scatter(gout) ; gfeat must be zero-initialised by caller
- * (or hold a gradient to accumulate into).                                  */
+/* gfeat (B,N,C) = scatter-add of gout through the saved arg-max (autograd of index + max).  gfeat is WRITTEN IN
+ * FULL (rows nobody selected are zero).  C % 4 == 0, C <= 512: gathered per source row in a fixed order —
+ * deterministic, no float atomics; other shapes: memset + float atomics.                                      */
 int hsp_gather_max_bwd(const float* gout, const int32_t* idx, const int32_t* rows,
                        const uint8_t* argmax, int B, int N, int C, int R, int kuse,
                        int kstride, float* gfeat, void* stream);
@@ -170,10 +171,11 @@ int hsp_orl_global_bwd(const float* gG, const int32_t* idx, const uint8_t* argma
 int hsp_upsample_rows_fwd(const float* feat, const int32_t* nn, int B, int Nsrc,
                           int M, int C, void* out, int ldo, int col0, int out_dtype,
                           void* stream);
-/* gfeat (B,Nsrc,C) += sum over i with nn[b,i]==r of gout[b,i,col0:col0+C]  (nn != NULL;
- * gfeat zero-initialised by the caller), or gfeat = gout[..., col0:col0+C] (nn == NULL,
- * Nsrc == M).  out / gout are fp32 or bf16 (HSP_DTYPE_*): the (B,M,ldo) concat
- * buffer feeds the bf16 tensor-core MLPs directly.                          */
+/* gfeat (B,Nsrc,C) = sum over i with nn[b,i]==r of gout[b,i,col0:col0+C]  (nn != NULL; written in full, rows
+ * without a target are zero; 16-byte aligned C % 8 == 0 slices are gathered per source row in ascending target
+ * order — deterministic, no float atomics; other shapes: memset + float atomics), or
+ * gfeat = gout[..., col0:col0+C] (nn == NULL, Nsrc == M).  out / gout are fp32 or bf16 (HSP_DTYPE_*): the
+ * (B,M,ldo) concat buffer feeds the bf16 tensor-core MLPs directly.                                           */
 int hsp_upsample_rows_bwd(const void* gout, const int32_t* nn, int B, int Nsrc,
                           int M, int C, int ldo, int col0, int gout_dtype, float* gfeat,
                           void* stream);
@@ -344,6 +346,32 @@ int hsp_augment(const float* PC, const float* R, const float* t, const float* s,
                 const float* gates, const float* ey, const float* defor, float p_bb, float p_rt,
                 float p_bc, float p_pc, float pc_r, int B, int N, int Nm, float* PC_out, float* R_out,
                 float* t_out, float* s_out, void* stream);
+
+/* Unit support directions: F.normalize(directions, dim=0) (gcn3d.py:95, :162) and its backward, one launch
+ * each.  d, out, g, gd (3, n) row-major fp32; nrm (n) = ||d[:, j]|| kept for the backward; eps = 1e-12.    */
+int hsp_normalize_cols_fwd(const float* d, int n, float eps, float* out, float* nrm, void* stream);
+int hsp_normalize_cols_bwd(const float* g, const float* out, const float* nrm, int n, float eps, float* gd,
+                           void* stream);
+
+/* ------------------------------------------------------------------ K11 --
+ * Input pre-stage: depth ROI -> camera-frame point cloud -> n_pts sampled points.
+ * hsp_depth_to_cloud replaces datasets/load_data.py:322-333 `_depth_to_pcl` followed by `/ 1000.0` (:277)
+ *   [camK_is_f64 = 1: numpy's float64 arithmetic, camK (B,3,3) double] and the back-projection of
+ *   network/point_sample/pc_sample.py:24-54 `PC_sample` [camK_is_f64 = 0: torch float32 arithmetic, camK float].
+ *   depth, mask (B,H,W) fp32; xymap (B,2,H,W) fp32 (x map, y map); a pixel is kept when depth > 0 and mask > 0.
+ *   cloud (B,H*W,3): the kept pixels in raster order, metres ((x - cx) * d / fx, (y - cy) * d / fy, d) / 1000;
+ *   rows >= count[b] are not written.  count (B) int32.
+ * hsp_sample_points replaces load_data.py:307-320 `_sample_points` / pc_sample.py:57-75:
+ *   choose (B,n_pts) int32 != NULL: out[b,i] = cloud[b, choose[b,i]] (the caller's numpy draw: exact parity);
+ *   choose == NULL: count <= n_pts -> out[b,i] = cloud[b, i mod count] (the reference's tile rule);
+ *                   count >  n_pts -> a uniformly random subset without replacement (counter-hash keys from
+ *                   `seed`, n_pts smallest), in raster order.
+ *   status (device int32, optional, OR-ed): bit 0 = an object without valid pixels (its rows are zeros),
+ *   bit 1 = a choose index outside [0, count) (clamped).                                                  */
+int hsp_depth_to_cloud(const float* depth, const float* mask, const float* xymap, const void* camK,
+                       int camK_is_f64, int B, int H, int W, float* cloud, int* count, void* stream);
+int hsp_sample_points(const float* cloud, const int* count, const int* choose, unsigned long long seed,
+                      int B, int cap, int n_pts, float* out, int* status, void* stream);
 
 /* fp32 -> bf16 multi-term split feeding hsp_gemm_bf16 for fp32-accurate contractions (the fp32 evaluation
  * forward, BASELINE configs[1]): out (M, nterms*Kpad) bf16, term t = component comp[t] (0: bf16(x),

@@ -379,11 +379,65 @@ def golden_optim():
     save("optim", **arrays)
 
 
+def golden_prestage(FLAGS):
+    """The reference's input pre-stage on synthetic depth ROIs: `PoseDataset._depth_to_pcl` + `/1000` +
+    `_sample_points` (datasets/load_data.py:277,307-333) and `PC_sample` (network/point_sample/pc_sample.py).
+    Shim: numpy >= 1.24 removed `np.float` (load_data.py:325 uses it); it is aliased to `float` here."""
+    np.float = float
+    from datasets.load_data import PoseDataset
+    from network.point_sample.pc_sample import PC_sample
+    rng = np.random.RandomState(5)
+    B, H, W = 4, 48, 64
+    n = int(FLAGS.random_points)
+    # depth in millimetres (uint16-valued), holes (0), an object mask of different sizes per object:
+    # object 0: > n valid pixels, 1: < n (tile / replace=True), 2: exactly structured, 3: few pixels
+    depth = (rng.randint(400, 1500, size=(B, H, W))).astype(np.float32)
+    depth[rng.rand(B, H, W) < 0.15] = 0.0
+    mask = np.zeros((B, H, W), dtype=np.float32)
+    mask[0, 4:44, 6:60] = 1.0
+    mask[1, 10:30, 12:40] = 1.0
+    mask[2, :, :] = (rng.rand(H, W) < 0.6)
+    mask[3, 20:23, 30:37] = 1.0
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    xymap = np.stack([xs * 2.5 + 100.25, ys * 2.5 + 60.5], 0).astype(np.float32)
+    xymap = np.repeat(xymap[None], B, 0) + rng.rand(B, 1, 1, 1).astype(np.float32) * 40
+    K = np.array([[577.5, 0, 319.5], [0, 577.5, 239.5], [0, 0, 1.0]])
+    camK = np.repeat(K[None], B, 0) + rng.rand(B, 3, 3) * np.array([[3.0, 0, 3.0], [0, 3.0, 3.0], [0, 0, 0]])
+    out = {"depth": depth, "mask": mask, "xymap": xymap, "camK64": camK, "n_pts": np.int64(n)}
+    # (a) the loader's functions (float64 arithmetic)
+    np.random.seed(123)
+    for b in range(B):
+        pcl = PoseDataset._depth_to_pcl(None, depth[b], camK[b], xymap[b], mask[b]) / 1000.0
+        out[f"pcl_{b}"] = pcl
+        total = pcl.shape[0]
+        if total > n:      # reproduce the draw _sample_points makes, and record it
+            st = np.random.get_state()
+            ids = np.random.permutation(total)[:n]
+            np.random.set_state(st)
+            out[f"ids_{b}"] = ids.astype(np.int32)
+        out[f"sampled_{b}"] = PoseDataset._sample_points(None, pcl, n)
+        assert out[f"sampled_{b}"].dtype == np.float32
+    # (b) PC_sample (torch float32), objects 0..2 (object 3 has > 1 pixel too, keep all four)
+    FLAGS.sample_method = "basic"
+    np.random.seed(321)
+    st = np.random.get_state()
+    PC = PC_sample(torch.from_numpy(mask)[:, None], torch.from_numpy(depth)[:, None],
+                   torch.from_numpy(camK.astype(np.float32)), torch.from_numpy(xymap))
+    out["PC_sample"] = PC
+    np.random.set_state(st)
+    chooses = []
+    for b in range(B):
+        l_all = int(((mask[b] * (depth[b] > 0)) > 0).sum())
+        chooses.append(np.random.choice(l_all, n, replace=l_all < n))
+    out["PC_choose"] = np.stack(chooses).astype(np.int32)
+    save("prestage", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     _args = sys.argv[1:]
     FLAGS, gcn3d = import_reference()
-    which = _args or ["knn", "ops", "e2e_eval", "e2e_train", "aug", "losses", "optim", "e2e_eval_b16"]
+    which = _args or ["knn", "ops", "e2e_eval", "e2e_train", "aug", "losses", "optim", "e2e_eval_b16", "prestage"]
     if "knn" in which:
         golden_knn(gcn3d)
     if "ops" in which:
@@ -400,3 +454,5 @@ if __name__ == "__main__":
         golden_losses(FLAGS)
     if "optim" in which:
         golden_optim()
+    if "prestage" in which:
+        golden_prestage(FLAGS)

@@ -74,8 +74,8 @@ def test_product_path_never_imports_the_oracle():
 
 def test_hspose_boundary_error_behaviour_and_build_params():
     """Reference conventions at the module boundary (network/HSPose.py:23-50,258-275,
-    engine/organize_loss.py:13): unknown stages raise NotImplementedError, a missing point cloud is
-    not silently sampled, build_params returns the single parameter group engine/train.py:47 expects."""
+    engine/organize_loss.py:13): unknown stages raise NotImplementedError, a missing point cloud
+    without a depth ROI to sample it from is an error (and the sampling has no CPU path), build_params returns the single parameter group engine/train.py:47 expects."""
     import hspose_b200.flags as hf
     from hspose_b200.HSPose import HSPose, control_loss
     with pytest.raises(NotImplementedError):
@@ -83,8 +83,12 @@ def test_hspose_boundary_error_behaviour_and_build_params():
     with pytest.raises(NotImplementedError):
         HSPose("no_such_stage")
     net = HSPose("PoseNet_only")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):
         net(PC=None, obj_id=torch.zeros(1))
+    from hspose_b200._lib import HSPoseLibraryError
+    with pytest.raises(HSPoseLibraryError):
+        net(depth=torch.ones(1, 1, 8, 8), def_mask=torch.ones(1, 1, 8, 8), camK=torch.eye(3)[None],
+            gt_2D=torch.zeros(1, 2, 8, 8), obj_id=torch.zeros(1))
     groups = net.build_params(training_stage_freeze=[])
     assert len(groups) == 1 and groups[0]["lr"] == float(hf.get_flags().lr) * hf.get_flags().lr_pose
     n = sum(p.numel() for p in groups[0]["params"])

@@ -600,3 +600,90 @@ def test_residual_sum_xyz_ste_mode(cuda):
     assert torch.allclose(out, ref, atol=1e-6)
     assert torch.allclose(W.grad, Wr.grad, atol=1e-4, rtol=1e-5)
     assert torch.equal(feat.grad, go) and torch.allclose(gp.grad, go.sum(1), atol=1e-4)
+
+
+# ----------------------------------------------------------------- direction normalisation, weight split
+def test_normalize_dirs_matches_F_normalize_fwd_bwd(cuda):
+    """ops.normalize_dirs == F.normalize(d, dim=0) (reference gcn3d.py:95, :162), values and gradient,
+    including a column below the eps clamp."""
+    import torch.nn.functional as F
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    for n in (7 * 128, 7 * 512, 5):
+        d0 = (torch.rand(3, n, generator=g) - 0.5) * 0.07
+        d0[:, 0] = 0.0                                   # clamped column
+        gout = torch.randn(3, n, generator=g)
+        a = d0.clone().to(cuda).requires_grad_(True)
+        b = d0.clone().to(cuda).requires_grad_(True)
+        ya, yb = ops.normalize_dirs(a), F.normalize(b, dim=0)
+        assert torch.allclose(ya, yb, atol=0, rtol=2e-7)
+        ya.backward(gout.to(cuda))
+        yb.backward(gout.to(cuda))
+        scale = b.grad[:, 1:].abs().max().item()
+        assert (a.grad[:, 1:] - b.grad[:, 1:]).abs().max().item() <= 2e-6 * scale
+        assert torch.equal(a.grad[:, 0], b.grad[:, 0])
+
+
+def test_split_halves_gradient_is_the_concatenation(cuda):
+    ops = _ops()
+    W = torch.randn(16, 32, device=cuda, requires_grad=True)
+    V = W.detach().clone().requires_grad_(True)
+    a, b = ops.split_halves(W, 16)
+    (a.sum() * 2 + (b * b).sum()).backward()
+    (V[:, :16].sum() * 2 + (V[:, 16:] ** 2).sum()).backward()
+    assert torch.equal(W.grad, V.grad)
+    W.grad = None
+    a, b = ops.split_halves(W, 16)
+    a.sum().backward()                                  # one half unused
+    assert torch.equal(W.grad[:, :16], torch.ones(16, 16, device=cuda)) and float(W.grad[:, 16:].abs().max()) == 0
+
+
+# ----------------------------------------------------------------- deterministic scatter backwards (K5b / K5c)
+@pytest.mark.parametrize("B,N,R,C", [(3, 1028, 257, 128), (2, 257, 64, 256), (2, 64, 16, 512), (2, 50, 13, 20)])
+def test_gather_max_and_upsample_backward_deterministic(cuda, B, N, R, C):
+    """Pool_layer / nearest up-sampling backward (autograd of gcn3d.py:39-47 `index` + max, FaceRecon.py:100-107):
+    equal to autograd of the oracle formulation and — being gathers over the source rows in a fixed order, not
+    float atomics — bit-identical from run to run, whatever junk the output buffer held before."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(B * N + C)
+    feat = torch.randn(B, N, C, generator=g)
+    idx = torch.stack([torch.stack([torch.randperm(N, generator=g)[:4] for _ in range(N)]) for _ in range(B)])
+    rows = torch.randperm(N, generator=g)[:R]
+    # reference: gather + max with autograd
+    fr = feat.clone().requires_grad_()
+    gathered = to.take_rows(fr, idx)[:, rows]                       # (B,R,4,C)
+    pooled = gathered.max(dim=2)[0]
+    go = torch.randn(pooled.shape, generator=g) * 1.7
+    pooled.backward(go)
+    fc = feat.to(cuda).requires_grad_()
+    out = ops.gather_max(fc, idx.to(cuda).int(), rows.to(cuda).int(), kuse=4)
+    assert np.array_equal(out.detach().cpu().numpy(), pooled.detach().numpy())
+    grads = []
+    for _ in range(3):
+        fc.grad = None
+        junk = torch.full((B, N, C), float("nan"), device=cuda)     # the allocator may hand this block to gfeat
+        del junk
+        out = ops.gather_max(fc, idx.to(cuda).int(), rows.to(cuda).int(), kuse=4)
+        out.backward(go.to(cuda))
+        grads.append(fc.grad.clone())
+    np.testing.assert_allclose(grads[0].cpu().numpy(), fr.grad.numpy(), atol=1e-5)
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+    # nearest up-sampling: M targets read R source rows; some source rows are read by nobody
+    M = 1028
+    src = torch.randn(B, R, C, generator=g)
+    nn = torch.randint(0, max(R - 2, 1), (B, M), generator=g)
+    sr = src.clone().requires_grad_()
+    up = to.take_rows(sr, nn[..., None]).squeeze(2)
+    gu = torch.randn(up.shape, generator=g) * 0.3
+    up.backward(gu)
+    grads = []
+    for _ in range(3):
+        sc = src.to(cuda).requires_grad_()
+        junk = torch.full((B, R, C), float("nan"), device=cuda)
+        del junk
+        ops.gather_rows(sc, nn.to(cuda).int()).backward(gu.to(cuda))
+        grads.append(sc.grad.clone())
+    np.testing.assert_allclose(grads[0].cpu().numpy(), sr.grad.numpy(), atol=2e-5)
+    if C % 8 == 0:       # (other widths take the float-atomics path: equal up to the order of the additions)
+        assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+    assert float(grads[0][:, R - 1].abs().max()) == 0.0 or R <= 2
