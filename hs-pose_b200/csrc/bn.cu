@@ -164,11 +164,12 @@ bn_reduce_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, int
   }
 }
 
-// Fixed-order sum of the per-CTA partials: one CTA of 256 threads owns BN_FC = 8 channels,
-// thread (cx = tid % 8, ry = tid / 8) adds chunks ry, ry+32, ... (independent loads, all in
-// flight at once), then the 32 group sums are added in order 0..31 by the ry == 0 threads
-// (deterministic).  C/8 CTAs: wide enough that the finalize costs a few microseconds.
-constexpr int BN_FC = 8, BN_FG = 32;
+// Fixed-order sum of the per-CTA partials: one CTA of 1024 threads owns BN_FC = 8 channels,
+// thread (cx = tid % 8, ry = tid / 8) adds chunks ry, ry+128, ... (<= 9 independent loads at
+// M = 131584, all in flight at once: the kernel is pure load latency, so it is kept to ONE round trip),
+// then the 128 group sums are added in a fixed order (16 threads per channel over 8 groups each,
+// then 16 in order) — deterministic.  Was 32 groups x 32 sequential loads: 12-13 us per call, 44 calls a step.
+constexpr int BN_FC = 8, BN_FG = 128;
 __device__ __forceinline__ bool bn_sum_partials(const float* __restrict__ partial, int rchunks,
                                                 int C, int& c, double& s, double& q, int ldp = 0) {
   if (ldp == 0) ldp = C;    // row pitch of a partial plane (>= C when the planes are column slices)
@@ -186,10 +187,18 @@ __device__ __forceinline__ bool bn_sum_partials(const float* __restrict__ partia
   sh[0][ry][cx] = a;
   sh[1][ry][cx] = b;
   __syncthreads();
+  if (ry < 16) {            // second level: groups 8 ry .. 8 ry + 7, in order
+    a = 0.0; b = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) { a += sh[0][8 * ry + g][cx]; b += sh[1][8 * ry + g][cx]; }
+  }
+  __syncthreads();
+  if (ry < 16) { sh[0][ry][cx] = a; sh[1][ry][cx] = b; }
+  __syncthreads();
   s = 0.0; q = 0.0;
   if (ry != 0 || c >= C) return false;
 #pragma unroll
-  for (int g = 0; g < BN_FG; ++g) { s += sh[0][g][cx]; q += sh[1][g][cx]; }
+  for (int g = 0; g < 16; ++g) { s += sh[0][g][cx]; q += sh[1][g][cx]; }
   return true;
 }
 

@@ -69,6 +69,126 @@ __global__ void chamfer_bwd_kernel(const float* __restrict__ a, const float* __r
   }
 }
 
+// Deterministic form (the default).  CTA = object (x a slice of its points): the inverse of the idx_b table — for
+// every a_i the b_j whose nearest neighbour it is, ascending j — is built in shared memory (count, scan, fill,
+// per-point insertion sort of the short lists), then thread = point a_i adds its own term and those of its list in
+// that fixed order and writes ga once: no float atomics, no memset, O(N + M) work per object.
+constexpr int CHB_THREADS = 512;
+constexpr int CHB_LONG = 24;      // lists longer than this are summed by the whole CTA
+constexpr int CHB_HEAVY = 512;    // >= M / CHB_LONG for every M the shared-memory tables admit
+__global__ void __launch_bounds__(CHB_THREADS)
+chamfer_bwd_det_kernel(const float* __restrict__ a, const float* __restrict__ b, const int32_t* __restrict__ idx_a,
+                       const int32_t* __restrict__ idx_b, const float* __restrict__ g_a,
+                       const float* __restrict__ g_b, int N, int M, int per, float* __restrict__ ga) {
+  extern __shared__ int32_t s_mem[];
+  int32_t* s_start = s_mem;                    // [N + 1]
+  int32_t* s_cur = s_mem + N + 1;              // [N]
+  int32_t* s_list = s_cur + N;                 // [M]
+  const int o = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int32_t* ib = idx_b + (size_t)o * M;
+  for (int v = tid; v < N; v += CHB_THREADS) s_cur[v] = 0;
+  __syncthreads();
+  for (int e = tid; e < M; e += CHB_THREADS) {
+    const int k = __ldg(ib + e);
+    if (k >= 0 && k < N) atomicAdd(&s_cur[k], 1);
+  }
+  __syncthreads();
+  if (tid < 32) {                              // exclusive scan of the counts, 32 at a time
+    int run = 0;
+    for (int v0 = 0; v0 < N; v0 += 32) {
+      const int v = v0 + lane;
+      const int c = v < N ? s_cur[v] : 0;
+      int inc = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (v < N) s_start[v] = run + inc - c;
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) s_start[N] = run;
+  }
+  __syncthreads();
+  for (int v = tid; v < N; v += CHB_THREADS) s_cur[v] = s_start[v];
+  __syncthreads();
+  for (int e = tid; e < M; e += CHB_THREADS) {
+    const int k = __ldg(ib + e);
+    if (k >= 0 && k < N) s_list[atomicAdd(&s_cur[k], 1)] = e;
+  }
+  __syncthreads();
+  __shared__ int s_heavy[CHB_HEAVY];
+  __shared__ int s_nheavy;
+  __shared__ float s_red[3][CHB_THREADS / 32];
+  if (tid == 0) s_nheavy = 0;
+  __syncthreads();
+  const int i_end = min(N, (int)(blockIdx.x + 1) * per);
+  for (int i = blockIdx.x * per + tid; i < i_end; i += CHB_THREADS) {
+    const int s0 = s_start[i], s1 = s_start[i + 1];
+    if (s1 - s0 > CHB_LONG) {                  // a point many b_j collapse onto: summed by the whole CTA below
+      const int slot = atomicAdd(&s_nheavy, 1);
+      if (slot < CHB_HEAVY) s_heavy[slot] = i;
+      continue;
+    }
+    for (int x = s0 + 1; x < s1; ++x) {        // the fill order is arbitrary: sort the (short) list
+      const int key = s_list[x];
+      int y = x - 1;
+      while (y >= s0 && s_list[y] > key) { s_list[y + 1] = s_list[y]; --y; }
+      s_list[y + 1] = key;
+    }
+    const size_t t = (size_t)o * N + i;
+    const float p[3] = {a[t * 3], a[t * 3 + 1], a[t * 3 + 2]};
+    const float* q = b + ((size_t)o * M + idx_a[t]) * 3;
+    const float w = 2.0f * g_a[t];
+    float acc[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) acc[d] = w * (p[d] - q[d]);
+    for (int x = s0; x < s1; ++x) {
+      const int j = s_list[x];
+      const float* bj = b + ((size_t)o * M + j) * 3;
+      const float wj = 2.0f * __ldg(g_b + (size_t)o * M + j);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) acc[d] -= wj * (__ldg(bj + d) - p[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) ga[t * 3 + d] = acc[d];
+  }
+  __syncthreads();
+  // heavy points: thread t owns the contiguous slice [t * chunk, (t + 1) * chunk) of the b_j (ascending j inside),
+  // lanes are combined by a shuffle tree and the warps in order 0..15 — a fixed order again
+  const int nheavy = min(s_nheavy, CHB_HEAVY);
+  const int chunk = (M + CHB_THREADS - 1) / CHB_THREADS;
+  for (int h = 0; h < nheavy; ++h) {
+    const int i = s_heavy[h];
+    const size_t t = (size_t)o * N + i;
+    const float p[3] = {a[t * 3], a[t * 3 + 1], a[t * 3 + 2]};
+    float acc[3] = {0.f, 0.f, 0.f};
+    const int j1 = min(M, (tid + 1) * chunk);
+    for (int j = tid * chunk; j < j1; ++j) {
+      if (__ldg(ib + j) == i) {
+        const float* bj = b + ((size_t)o * M + j) * 3;
+        const float wj = 2.0f * __ldg(g_b + (size_t)o * M + j);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) acc[d] -= wj * (__ldg(bj + d) - p[d]);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) acc[d] += __shfl_down_sync(0xffffffffu, acc[d], sft);
+      if (lane == 0) s_red[d][tid >> 5] = acc[d];
+    }
+    __syncthreads();
+    if (tid < 3) {
+      const float* q = b + ((size_t)o * M + idx_a[t]) * 3;
+      float r = 2.0f * g_a[t] * (p[tid] - q[tid]);
+      for (int w = 0; w < CHB_THREADS / 32; ++w) r += s_red[tid][w];
+      ga[t * 3 + tid] = r;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace hsp
 
 extern "C" int hsp_chamfer_fwd(const float* a, const float* b, int B, int N, int M,
@@ -99,6 +219,18 @@ extern "C" int hsp_chamfer_bwd(const float* a, const float* b, const int32_t* id
     return HSP_EINVAL;
   if (B == 0) return HSP_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  const size_t sm_a = ((size_t)2 * N + 1 + M) * sizeof(int32_t), sm_b = ((size_t)2 * M + 1 + N) * sizeof(int32_t);
+  if (sm_a <= 48 * 1024 && sm_b <= 48 * 1024 && B <= 65535) {
+    const int gxa = (N + 2 * CHB_THREADS - 1) / (2 * CHB_THREADS), gxb = (M + 2 * CHB_THREADS - 1) / (2 * CHB_THREADS);
+    chamfer_bwd_det_kernel<<<dim3(gxa, B), CHB_THREADS, sm_a, st>>>(a, b, idx_a, idx_b, gdist_a, gdist_b, N, M,
+                                                                   (N + gxa - 1) / gxa, ga);
+    HSP_LAUNCH_CHECK();
+    chamfer_bwd_det_kernel<<<dim3(gxb, B), CHB_THREADS, sm_b, st>>>(b, a, idx_b, idx_a, gdist_b, gdist_a, M, N,
+                                                                   (M + gxb - 1) / gxb, gb);
+    HSP_LAUNCH_CHECK();
+    return HSP_OK;
+  }
+  // very large clouds: float atomics (order-dependent in the last bit)
   if (cudaMemsetAsync(ga, 0, sizeof(float) * (size_t)B * N * 3, st) != cudaSuccess ||
       cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)B * M * 3, st) != cudaSuccess)
     return HSP_ELAUNCH;

@@ -58,54 +58,71 @@ gather_max_bwd_kernel(const float* __restrict__ gout, const int32_t* __restrict_
 // the matching output gradients, where the saved arg-max names that slot, in ascending (r, slot) order.  Every
 // gfeat row is written exactly once: no float atomics, no zero-fill, bit-reproducible.
 constexpr int GMB_WARPS = 8;
+constexpr int GMB_ROWS = 8;                    // source rows per warp: the table staging is amortised over 64 rows
 constexpr int GMB_MAXV = 4;                    // float4 accumulators per lane: C <= 512
 __global__ void __launch_bounds__(GMB_WARPS * 32)
 gather_max_bwd_det_kernel(const float* __restrict__ gout, const int32_t* __restrict__ idx,
                           const int32_t* __restrict__ rows, const uint8_t* __restrict__ argmax, int N, int C,
                           int R, int kuse, int kstride, float* __restrict__ gfeat) {
-  extern __shared__ int32_t s_tab[];           // [R * kuse]
+  extern __shared__ __align__(16) int32_t s_tab[];   // [R * kuse], padded to a multiple of 4 with -1
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int T = R * kuse;
-  for (int t = threadIdx.x; t < T; t += GMB_WARPS * 32) {
-    const int r = t / kuse, sl = t - r * kuse;
-    const int i = rows ? __ldg(rows + r) : r;
-    s_tab[t] = __ldg(idx + ((size_t)b * N + i) * kstride + sl);
+  const int T = R * kuse, T4 = (T + 3) >> 2;
+  for (int t = threadIdx.x; t < 4 * T4; t += GMB_WARPS * 32) {
+    int v = -1;
+    if (t < T) {
+      const int r = t / kuse, sl = t - r * kuse;
+      const int i = rows ? __ldg(rows + r) : r;
+      v = __ldg(idx + ((size_t)b * N + i) * kstride + sl);
+    }
+    s_tab[t] = v;
   }
   __syncthreads();
-  const int j = blockIdx.x * GMB_WARPS + warp;
-  if (j >= N) return;
+  const int4* tab4 = reinterpret_cast<const int4*>(s_tab);
   const int c4 = C >> 2;
-  float4 acc[GMB_MAXV];
+  for (int rr = 0; rr < GMB_ROWS; ++rr) {
+    const int j = (blockIdx.x * GMB_WARPS + warp) * GMB_ROWS + rr;
+    if (j >= N) return;
+    float4 acc[GMB_MAXV];
 #pragma unroll
-  for (int v = 0; v < GMB_MAXV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int t0 = 0; t0 < T; t0 += 32) {
-    const int t = t0 + lane;
-    unsigned m = __ballot_sync(0xffffffffu, t < T && s_tab[t] == j);
-    while (m) {
-      const int tt = t0 + __ffs(m) - 1;
-      m &= m - 1;
-      const int r = tt / kuse;
-      const uint32_t sl = (uint32_t)(tt - r * kuse);
-      const size_t o = ((size_t)b * R + r) * C;
+    for (int v = 0; v < GMB_MAXV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q0 = 0; q0 < T4; q0 += 32) {      // 128 table entries per step
+      unsigned hit = 0;
+      if (q0 + lane < T4) {
+        const int4 e = tab4[q0 + lane];
+        hit = (e.x == j ? 1u : 0u) | (e.y == j ? 2u : 0u) | (e.z == j ? 4u : 0u) | (e.w == j ? 8u : 0u);
+      }
+      unsigned any = __ballot_sync(0xffffffffu, hit != 0u);
+      while (any) {                             // ascending (r, slot) order
+        const int L = __ffs(any) - 1;
+        any &= any - 1;
+        unsigned h = __shfl_sync(0xffffffffu, hit, L);
+        while (h) {
+          const int tt = 4 * (q0 + L) + __ffs(h) - 1;
+          h &= h - 1;
+          const int r = tt / kuse;
+          const uint32_t sl = (uint32_t)(tt - r * kuse);
+          const size_t o = ((size_t)b * R + r) * C;
 #pragma unroll
-      for (int v = 0; v < GMB_MAXV; ++v) {
-        const int q = lane + 32 * v;
-        if (q < c4) {
-          const uint32_t am = __ldg(reinterpret_cast<const uint32_t*>(argmax + o) + q);
-          const float4 g = __ldg(reinterpret_cast<const float4*>(gout + o) + q);
-          if ((am & 0xffu) == sl) acc[v].x += g.x;
-          if (((am >> 8) & 0xffu) == sl) acc[v].y += g.y;
-          if (((am >> 16) & 0xffu) == sl) acc[v].z += g.z;
-          if ((am >> 24) == sl) acc[v].w += g.w;
+          for (int v = 0; v < GMB_MAXV; ++v) {
+            const int q = lane + 32 * v;
+            if (q < c4) {
+              const uint32_t am = __ldg(reinterpret_cast<const uint32_t*>(argmax + o) + q);
+              const float4 g = __ldg(reinterpret_cast<const float4*>(gout + o) + q);
+              if ((am & 0xffu) == sl) acc[v].x += g.x;
+              if (((am >> 8) & 0xffu) == sl) acc[v].y += g.y;
+              if (((am >> 16) & 0xffu) == sl) acc[v].z += g.z;
+              if ((am >> 24) == sl) acc[v].w += g.w;
+            }
+          }
         }
       }
     }
-  }
-  float4* dst = reinterpret_cast<float4*>(gfeat + ((size_t)b * N + j) * C);
+    float4* dst = reinterpret_cast<float4*>(gfeat + ((size_t)b * N + j) * C);
 #pragma unroll
-  for (int v = 0; v < GMB_MAXV; ++v) {
-    const int q = lane + 32 * v;
-    if (q < c4) dst[q] = acc[v];
+    for (int v = 0; v < GMB_MAXV; ++v) {
+      const int q = lane + 32 * v;
+      if (q < c4) dst[q] = acc[v];
+    }
   }
 }
 
@@ -338,37 +355,48 @@ upsample_bwd_vec_kernel(const TO* __restrict__ gout, const int32_t* __restrict__
 // of the targets that map to j in ascending target order.  Every gfeat row is written exactly once (zeros when no
 // target maps to it): no float atomics, no zero-fill, bit-reproducible.
 constexpr int UBD_WARPS = 8;
-constexpr int UBD_ROWS = 2;                    // source rows per warp
+constexpr int UBD_ROWS = 4;                    // source rows per warp
 constexpr int UBD_MAXV = 4;                    // 8-channel vectors per lane: C <= 1024
 template <typename TO>
 __global__ void __launch_bounds__(UBD_WARPS * 32)
 upsample_bwd_det_kernel(const TO* __restrict__ gout, const int32_t* __restrict__ nn, int Nsrc, int M, int C,
                         int ldo, int col0, float* __restrict__ gfeat) {
-  extern __shared__ int32_t s_nn[];            // [M]
+  extern __shared__ __align__(16) int32_t s_nn[];    // [M], padded to a multiple of 4 with -1
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c8 = C >> 3;
-  for (int t = threadIdx.x; t < M; t += UBD_WARPS * 32) s_nn[t] = __ldg(nn + (size_t)b * M + t);
+  const int M4 = (M + 3) >> 2;
+  for (int t = threadIdx.x; t < 4 * M4; t += UBD_WARPS * 32) s_nn[t] = t < M ? __ldg(nn + (size_t)b * M + t) : -1;
   __syncthreads();
+  const int4* nn4 = reinterpret_cast<const int4*>(s_nn);
   for (int rr = 0; rr < UBD_ROWS; ++rr) {
     const int j = (blockIdx.x * UBD_WARPS + warp) * UBD_ROWS + rr;
     if (j >= Nsrc) return;
     float4 aa[UBD_MAXV], ab[UBD_MAXV];
 #pragma unroll
     for (int v = 0; v < UBD_MAXV; ++v) aa[v] = ab[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t0 = 0; t0 < M; t0 += 32) {
-      const int t = t0 + lane;
-      unsigned m = __ballot_sync(0xffffffffu, t < M && s_nn[t] == j);
-      while (m) {
-        const int i = t0 + __ffs(m) - 1;
-        m &= m - 1;
-        const TO* src = gout + ((size_t)b * M + i) * ldo + col0;
+    for (int q0 = 0; q0 < M4; q0 += 32) {      // 128 targets per step
+      unsigned hit = 0;
+      if (q0 + lane < M4) {
+        const int4 e = nn4[q0 + lane];
+        hit = (e.x == j ? 1u : 0u) | (e.y == j ? 2u : 0u) | (e.z == j ? 4u : 0u) | (e.w == j ? 8u : 0u);
+      }
+      unsigned any = __ballot_sync(0xffffffffu, hit != 0u);
+      while (any) {                             // ascending target order
+        const int L = __ffs(any) - 1;
+        any &= any - 1;
+        unsigned h = __shfl_sync(0xffffffffu, hit, L);
+        while (h) {
+          const int i = 4 * (q0 + L) + __ffs(h) - 1;
+          h &= h - 1;
+          const TO* src = gout + ((size_t)b * M + i) * ldo + col0;
 #pragma unroll
-        for (int v = 0; v < UBD_MAXV; ++v) {
-          const int q = lane + 32 * v;
-          if (q < c8) {
-            float4 a, c;
-            Out8<TO>::load(src + 8 * q, a, c);
-            aa[v].x += a.x; aa[v].y += a.y; aa[v].z += a.z; aa[v].w += a.w;
-            ab[v].x += c.x; ab[v].y += c.y; ab[v].z += c.z; ab[v].w += c.w;
+          for (int v = 0; v < UBD_MAXV; ++v) {
+            const int q = lane + 32 * v;
+            if (q < c8) {
+              float4 a, c;
+              Out8<TO>::load(src + 8 * q, a, c);
+              aa[v].x += a.x; aa[v].y += a.y; aa[v].z += a.z; aa[v].w += a.w;
+              ab[v].x += c.x; ab[v].y += c.y; ab[v].z += c.z; ab[v].w += c.w;
+            }
           }
         }
       }
@@ -459,9 +487,10 @@ extern "C" int hsp_gather_max_bwd(const float* gout, const int32_t* idx, const i
   if (B == 0) return HSP_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t tab = (size_t)R * kuse * sizeof(int32_t);
-  if (R > 0 && (C % 4) == 0 && C <= 128 * GMB_MAXV && tab <= 48 * 1024 && ((uintptr_t)gout % 16) == 0 &&
+  if (R > 0 && (C % 4) == 0 && C <= 128 * GMB_MAXV && tab + 16 <= 48 * 1024 && ((uintptr_t)gout % 16) == 0 &&
       ((uintptr_t)gfeat % 16) == 0 && ((uintptr_t)argmax % 4) == 0) {
-    gather_max_bwd_det_kernel<<<dim3((N + GMB_WARPS - 1) / GMB_WARPS, B), GMB_WARPS * 32, tab, st>>>(
+    gather_max_bwd_det_kernel<<<dim3((N + GMB_WARPS * GMB_ROWS - 1) / (GMB_WARPS * GMB_ROWS), B), GMB_WARPS * 32,
+                                tab + 16, st>>>(
         gout, idx, rows, argmax, N, C, R, kuse, kstride, gfeat);
     HSP_LAUNCH_CHECK();
     return HSP_OK;
@@ -574,10 +603,10 @@ extern "C" int hsp_upsample_rows_bwd(const void* gout, const int32_t* nn, int B,
   if (B == 0) return HSP_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = vec8_ok(gout, gfeat, C, ldo, col0, gout_dtype == HSP_DTYPE_BF16 ? 2 : 4);
-  if (nn && M > 0 && vec && C <= 256 * UBD_MAXV && (size_t)M * sizeof(int32_t) <= 48 * 1024) {
+  if (nn && M > 0 && vec && C <= 256 * UBD_MAXV && (size_t)M * sizeof(int32_t) + 16 <= 48 * 1024) {
     // scatter-add as a gather over the source rows: deterministic, writes every gfeat row once
     dim3 gd((Nsrc + UBD_WARPS * UBD_ROWS - 1) / (UBD_WARPS * UBD_ROWS), B);
-    const size_t sm = (size_t)M * sizeof(int32_t);
+    const size_t sm = (size_t)M * sizeof(int32_t) + 16;
     if (gout_dtype == HSP_DTYPE_BF16)
       upsample_bwd_det_kernel<__nv_bfloat16><<<gd, UBD_WARPS * 32, sm, st>>>((const __nv_bfloat16*)gout, nn, Nsrc, M, C,
                                                                          ldo, col0, gfeat);

@@ -355,6 +355,31 @@ def test_chamfer_vs_oracle(cuda):
     np.testing.assert_allclose(bc.grad.cpu().numpy(), b.grad.numpy(), atol=1e-6)
 
 
+def test_chamfer_backward_collapsed_cloud_deterministic(cuda):
+    """A collapsed reconstruction (what a randomly initialised recon head emits): hundreds of points share one
+    nearest neighbour.  The backward sums those long lists with the whole CTA in a fixed order — equal to autograd
+    of the materialised formulation and bit-identical from run to run."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(10)
+    a = (torch.randn(2, 1028, 3, generator=g) * 0.05)
+    b = a[:, 5:6, :] + torch.randn(2, 1028, 3, generator=g) * 1e-4          # every b_j sits on a_5 ...
+    b[:, 900:] = torch.randn(2, 128, 3, generator=g) * 0.05                  # ... except a spread-out tail
+    a, b = a.requires_grad_(), b.detach().requires_grad_()
+    d = ((a[:, :, None, :] - b[:, None, :, :]) ** 2).sum(-1)
+    (d.min(dim=2)[0].mean() + d.min(dim=1)[0].mean()).backward()
+    grads = []
+    for _ in range(3):
+        ac, bc = a.detach().to(cuda).requires_grad_(), b.detach().to(cuda).requires_grad_()
+        gda, gdb, _, gib = ops.chamfer(ac, bc)
+        (gda.mean() + gdb.mean()).backward()
+        grads.append((ac.grad.clone(), bc.grad.clone()))
+    assert int((gib[0] == 5).sum()) > 800
+    np.testing.assert_allclose(grads[0][0].cpu().numpy(), a.grad.numpy(), atol=2e-6)
+    np.testing.assert_allclose(grads[0][1].cpu().numpy(), b.grad.numpy(), atol=1e-6)
+    for ga, gb in grads[1:]:
+        assert torch.equal(ga, grads[0][0]) and torch.equal(gb, grads[0][1])
+
+
 # ----------------------------------------------------------------- K6b (BatchNorm + ReLU)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("M,C,ld,relu", [(4112, 128, 128, True), (1028, 256, 3584, True),

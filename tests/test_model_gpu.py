@@ -568,3 +568,40 @@ def test_eval_runner_buckets_and_generate_RT(cuda, golden):
         assert sorted(runner.graphs) == [1, 4, 8]
     finally:
         F.train, F.gcn_n_num = 1, 20
+
+
+def test_amp_train_gradients_are_bit_reproducible(cuda):
+    """SURVEY.md §5 (sort/segment based rather than float atomics): on the mixed-precision train path every backward
+    kernel adds in a fixed order (K4b fixed-point slabs, gathered pool / up-sample / Chamfer backward, fixed-order
+    reductions), so two runs of the same forward + backward give bit-identical gradients for ALL parameters."""
+    from hspose_b200 import parallel
+    from hspose_b200.HSPose import HSPose
+    F = _flags()
+    saved = {n: getattr(F, n) for n in ("aug_pc_pro", "aug_rt_pro", "aug_bb_pro", "aug_bc_pro", "train", "gcn_n_num")}
+    for n in ("aug_pc_pro", "aug_rt_pro", "aug_bb_pro", "aug_bc_pro"):
+        setattr(F, n, 0.0)
+    F.train, F.gcn_n_num = 1, 20
+    try:
+        model = fill_params(HSPose("PoseNet_only", chamfer_w=1.0)).to(cuda).train()
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        batch = {k: v.to(cuda) for k, v in synth_batch(6, 1028, seed=9, train=True).items()}
+        runs = []
+        for r in range(3):
+            parallel.seed_all(4321)
+            for p in model.parameters():
+                p.grad = None
+            junk = torch.randn(1 << (20 + r), device=cuda)      # shift the allocator between the runs
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                _, losses = model(**batch, do_loss=True)
+            total = sum(v.reshape(()).float() for grp in losses.values() for v in grp.values())
+            total.backward()
+            del junk
+            runs.append({n: p.grad.detach().clone() for n, p in model.posenet.named_parameters() if p.grad is not None})
+        assert len(runs[0]) > 100
+        bad = [n for n in runs[0] if not (torch.equal(runs[0][n], runs[1][n]) and torch.equal(runs[0][n], runs[2][n]))]
+        assert not bad, bad
+    finally:
+        for n, v in saved.items():
+            setattr(F, n, v)
