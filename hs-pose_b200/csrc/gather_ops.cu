@@ -57,8 +57,8 @@ gather_max_bwd_kernel(const float* __restrict__ gout, const int32_t* __restrict_
 // -> source table (R x kuse ints) sits in shared memory; the warp scans it 32 entries at a time (ballot) and adds
 // the matching output gradients, where the saved arg-max names that slot, in ascending (r, slot) order.  Every
 // gfeat row is written exactly once: no float atomics, no zero-fill, bit-reproducible.
-constexpr int GMB_WARPS = 8;
-constexpr int GMB_ROWS = 8;                    // source rows per warp: the table staging is amortised over 64 rows
+constexpr int GMB_WARPS = 16;
+constexpr int GMB_ROWS = 2;                    // source rows per warp: the table staging is amortised over 32 rows
 constexpr int GMB_MAXV = 4;                    // float4 accumulators per lane: C <= 512
 __global__ void __launch_bounds__(GMB_WARPS * 32)
 gather_max_bwd_det_kernel(const float* __restrict__ gout, const int32_t* __restrict__ idx,
@@ -354,8 +354,8 @@ upsample_bwd_vec_kernel(const TO* __restrict__ gout, const int32_t* __restrict__
 // nearest table (M ints) sits in shared memory; the warp scans it 32 targets at a time (ballot) and adds the rows
 // of the targets that map to j in ascending target order.  Every gfeat row is written exactly once (zeros when no
 // target maps to it): no float atomics, no zero-fill, bit-reproducible.
-constexpr int UBD_WARPS = 8;
-constexpr int UBD_ROWS = 4;                    // source rows per warp
+constexpr int UBD_WARPS = 16;
+constexpr int UBD_ROWS = 1;                    // source rows per warp
 constexpr int UBD_MAXV = 4;                    // 8-channel vectors per lane: C <= 1024
 template <typename TO>
 __global__ void __launch_bounds__(UBD_WARPS * 32)

@@ -88,9 +88,18 @@ def _geo_index32_exact(vertices, k):
     return table if kk == k else table[:, :, :k].contiguous()
 
 
+def _checked_index(index, n_rows, what):
+    """Caller-supplied neighbour / row indices are range-checked before a kernel dereferences them (PyTorch's
+    own indexing raises for these; the kernels would read out of bounds).  One host sync — only on the API-parity
+    functions and the teacher-forcing hook, never on the indices the library computes itself."""
+    if index.numel() and (int(index.min()) < 0 or int(index.max()) >= n_rows):
+        raise IndexError(f"{what}: index out of range [0, {n_rows})")
+    return index
+
+
 def _feature_index32(feature_map, k):
     if _forced_rf is not None:
-        idx = _forced_rf.pop(0)
+        idx = _checked_index(_forced_rf.pop(0), feature_map.shape[1], "force_rf_indices")
         idx32 = idx.to(device=feature_map.device, dtype=torch.int32).contiguous()
     else:
         idx32 = ops.knn_feat(feature_map, k)[1]
@@ -117,12 +126,14 @@ def indexing_neighbor_new(tensor: "(bs, vertice_num, dim)", index: "(bs, v_out, 
     """Reference gcn3d.py:39-47 (materialising form, API parity only — the fused
     kernels never call it).  Return: (bs, v_out, neighbor_num, dim)."""
     bs, v_out, n = index.shape
+    _checked_index(index, tensor.shape[1], "indexing_neighbor_new")
     rows = ops.gather_rows(tensor, index.reshape(bs, v_out * n).to(torch.int32))
     return rows.view(bs, v_out, n, tensor.shape[2])
 
 
 def get_neighbor_direction_norm(vertices, neighbor_index, return_unnormed=False):
     """Reference gcn3d.py:49-59.  Return: (bs, vertice_num, neighbor_num, 3) fp32."""
+    _checked_index(neighbor_index, vertices.shape[1], "get_neighbor_direction_norm")
     return ops.direction_norm(vertices, neighbor_index.to(torch.int32), return_unnormed)
 
 

@@ -140,6 +140,15 @@ def direction_norm(xyz, idx32, return_unnormed=False):
 
 
 # ------------------------------------------------------------ graph convs
+def _no_xyz_grad(ctx):
+    """The reference graph is differentiable w.r.t. the vertices through F.normalize(neighbours - vertices); the
+    fused kernels do not produce that gradient (the network's input cloud is detached, HSPose.py:53).  A caller
+    whose coordinates require grad gets an error instead of a silently missing gradient."""
+    if ctx.needs_input_grad[0]:
+        raise NotImplementedError("hs-pose_b200: the gradient w.r.t. the point coordinates (xyz) is not implemented; "
+                                  "detach the cloud (the reference detaches it, network/HSPose.py:53)")
+
+
 class _NormalizeCols(torch.autograd.Function):
     """F.normalize(d, dim=0) for the (3, S*C) support directions, one launch each way."""
 
@@ -197,6 +206,7 @@ class _SurfaceConv(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, xyz, idx32, dirn, S, C):
+        _no_xyz_grad(ctx)
         xyz = _need(xyz, torch.float32, "xyz")
         idx32 = _need(idx32, torch.int32, "idx")
         dirn = _need(dirn, torch.float32, "dirn")
@@ -275,6 +285,7 @@ class _GraphConv(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, xyz, idx32, dirn, P, S, C):
+        _no_xyz_grad(ctx)
         xyz = _need(xyz, torch.float32, "xyz")
         idx32 = _need(idx32, torch.int32, "idx")
         dirn = _need(dirn, torch.float32, "dirn")
@@ -310,6 +321,7 @@ class _HSConvMixed(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xyz, idx32, dirn, fm, W, bias, S, C):
+        _no_xyz_grad(ctx)
         xyz = _need(xyz, torch.float32, "xyz")
         idx32 = _need(idx32, torch.int32, "idx")
         dirn = _need(dirn, torch.float32, "dirn")

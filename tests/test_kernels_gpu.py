@@ -712,3 +712,24 @@ def test_gather_max_and_upsample_backward_deterministic(cuda, B, N, R, C):
     if C % 8 == 0:       # (other widths take the float-atomics path: equal up to the order of the additions)
         assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
     assert float(grads[0][:, R - 1].abs().max()) == 0.0 or R <= 2
+
+
+def test_boundary_errors_index_range_and_xyz_grad(cuda):
+    """Error behaviour at the module boundary: caller-supplied indices out of range raise IndexError (PyTorch's
+    indexing would), and coordinates that require grad raise instead of silently getting no gradient."""
+    from hspose_b200 import gcn3d
+    ops = _ops()
+    v = torch.randn(2, 40, 3, device=cuda)
+    f = torch.randn(2, 40, 16, device=cuda)
+    bad = torch.randint(0, 40, (2, 40, 5), device=cuda)
+    bad[1, 3, 2] = 40
+    with pytest.raises(IndexError):
+        gcn3d.indexing_neighbor_new(f, bad)
+    with pytest.raises(IndexError):
+        gcn3d.get_neighbor_direction_norm(v, bad)
+    idx = ops.knn3(v, v, 5)[1]
+    dirn = torch.nn.functional.normalize(torch.randn(3, 7 * 16, device=cuda), dim=0).requires_grad_()
+    with pytest.raises(NotImplementedError):
+        ops.surface_conv(v.clone().requires_grad_(), idx, dirn, 7, 16)
+    ops.surface_conv(v, idx, dirn, 7, 16).sum().backward()        # the supported case still works
+    assert dirn.grad is not None

@@ -18,7 +18,7 @@ wc -l gpurun_out/launches_$TAG.csv
 python tools/summarize_launches.py gpurun_out/launches_$TAG.csv 2 > gpurun_out/${TAG}_launches_summary.txt 2>/dev/null
 gzip -f -k gpurun_out/launches_$TAG.csv
 timeout 1500 ncu --profile-from-start off --set full --clock-control none --import-source on \
-   -k regex:'gemm_tc|losses_|optim_|augment|split_bf16|knn|graph_conv|surface_conv|orl_|bn_|upsample|residual|gather_max|chamfer|kf_|dir_reduce|sqnorm|colmax|pair_dirs|absmax' -c 420 -f -o gpurun_out/prof_$TAG python tools/ncu_step.py 128 bf16 > gpurun_out/ncu_full_$TAG.log 2>&1
+   -k regex:'gemm_tc|losses_|optim_|augment|split_bf16|knn|graph_conv|surface_conv|orl_|bn_|upsample|residual|gather_max|chamfer|kf_|dir_reduce|sqnorm|colmax|pair_dirs|absmax|normalize_cols' -c 420 -f -o gpurun_out/prof_$TAG python tools/ncu_step.py 128 bf16 > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_full_$TAG.log
 python tools/ncu_summary.py gpurun_out/prof_$TAG.ncu-rep gpurun_out/${TAG}_ncu_full_summary.md gpurun_out/${TAG}_kernel_traffic.json > /dev/null 2>&1
 # the GEMM kernel's source-level stall reasons (needs -lineinfo): keep only a compact extract
