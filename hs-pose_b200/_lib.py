@@ -47,6 +47,8 @@ SIGNATURES = {
     "hsp_gemm_debug": (c_int, [c_int]),
     "hsp_gemm_bf16": (c_int, [P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int,
                               c_int, c_int, P, c_int, c_int, P]),
+    "hsp_gemm_bf16_acc": (c_int, [P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int, P,
+                                  c_int, c_int, c_int, P, c_int, c_int, P]),
     "hsp_losses_num_terms": (c_int, []),
     "hsp_losses_num_sums": (c_int, []),
     "hsp_losses_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, P, P, P]),

@@ -218,6 +218,8 @@ struct Params {
   int rows_per_group;
   float* stats;         // (ceil(M/128), 2, N) per-row-block column sums / sums of squares, or NULL
   int relu;             // epilogue: max(0, .) after the biases
+  const float* c_in;    // (M, ldc) fp32 or NULL: residual added to the product (fp32 output, splits == 1) — a dgrad
+  int ldc;              // whose result joins an existing gradient needs no separate add pass
   int debug;            // diagnostics (hsp_gemm_debug): 1 = no staging writes / stores, 2 = no MMAs, 4 = no TMA loads
 };
 
@@ -432,6 +434,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (EXTRA && p.bias_rows != nullptr && (full_rows || row_ok))
           brow = p.bias_rows + (size_t)((m0 + row) / p.rows_per_group) * p.N + n0 + ch * OUT_COLS;
         const bool brow_vec = n0 + (ch + 1) * OUT_COLS <= p.N;     // whole chunk inside the matrix: vector loads
+        const float* crow = nullptr;                               // residual row segment of this thread (fp32 output)
+        if (EXTRA && OUT_F32 && p.c_in != nullptr && (full_rows || row_ok))
+          crow = p.c_in + (size_t)(m0 + row) * p.ldc + n0 + ch * OUT_COLS;
         const float lo = (EXTRA && p.relu) ? 0.f : -INFINITY;
         const uint32_t srow = smem_u32(so) + row * 128;
         if (OUT_F32) {
@@ -447,6 +452,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (brow && (brow_vec || n0 + ch * OUT_COLS + 4 * j < p.N)) {      // N % 8 == 0: groups are all in or out
                 const float4 r4 = __ldg(reinterpret_cast<const float4*>(brow) + j);
                 o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+              }
+              if (crow && n0 + ch * OUT_COLS + 4 * j < p.N) {                    // N % 4 == 0 (checked by the host)
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(crow) + j);
+                o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w;
               }
               o.x = fmaxf(o.x, lo); o.y = fmaxf(o.y, lo); o.z = fmaxf(o.z, lo); o.w = fmaxf(o.w, lo);
             }
@@ -634,9 +643,19 @@ extern "C" int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void*
                              int N, int K, const float* bias, const float* bias_rows, int rows_per_group, int relu,
                              void* out, int ldo, int out_f32, int splits, float* stats, int tile_n, int ctas,
                              void* stream) {
+  return hsp_gemm_bf16_acc(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, bias, bias_rows, rows_per_group, relu,
+                           nullptr, 0, out, ldo, out_f32, splits, stats, tile_n, ctas, stream);
+}
+
+extern "C" int hsp_gemm_bf16_acc(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M,
+                                 int N, int K, const float* bias, const float* bias_rows, int rows_per_group,
+                                 int relu, const float* c_in, int ldc, void* out, int ldo, int out_f32, int splits,
+                                 float* stats, int tile_n, int ctas, void* stream) {
   using namespace hsp;
   using namespace hsp::gemm;
   if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0 || splits < 1) return HSP_EINVAL;
+  if (c_in && (!out_f32 || splits != 1 || (N % 4) != 0 || ldc < N || (ldc % 4) != 0 || ((uintptr_t)c_in % 16) != 0))
+    return HSP_EINVAL;
   const int oes = out_f32 ? 4 : 2;
   if (((uintptr_t)A % 16) || ((uintptr_t)B % 16) || ((uintptr_t)out % 16) || (lda * 2) % 16 || (ldb * 2) % 16 ||
       (ldo * oes) % 16)
@@ -672,9 +691,10 @@ extern "C" int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void*
   p.bias = bias; p.stats = stats;
   p.bias_rows = bias_rows; p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
   p.relu = relu ? 1 : 0;
+  p.c_in = c_in; p.ldc = ldc;
   p.debug = g_gemm_debug;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool extra = bias_rows != nullptr || relu != 0;   // the epilogue variant with the row-group bias / ReLU code
+  const bool extra = bias_rows != nullptr || relu != 0 || c_in != nullptr;   // the epilogue variant with the row-group bias / ReLU / residual code
 #define HSP_GEMM_CASE(BN_, CT_)                                                          \
   if (tile_n == BN_ && ctas == CT_)                                                      \
     return out_f32 ? (extra ? launch<BN_, CT_, true, true>(tA, tB, tO, p, sms, st)      \

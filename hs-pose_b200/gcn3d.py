@@ -11,6 +11,7 @@ There is no CPU path: CPU tensors raise HSPoseLibraryError.
 """
 import contextlib
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -149,6 +150,9 @@ def get_receptive_fields(neighbor_num, vertices, feature_map=None, mode='RF-F'):
     return get_neighbor_direction_norm(vertices, neighbor_index), neighbor_index
 
 
+_ORL_ONE_NODE = os.environ.get("HSP_ORL_ONE_NODE", "1") != "0"    # A/B switch (tools/, tests)
+
+
 def get_ORL_global(feature, vertices, neighbor_num):
     """Reference gcn3d.py:211-218.  Return: (bs, vertice_num, C) (per-object constant, repeated)."""
     G = ops.orl_global(feature, _geo_index32_exact(vertices, neighbor_num))
@@ -160,8 +164,15 @@ def _orl_fuse(feature, vertices, neighbor_num, conv2_weight, f_STE=None, ste_xyz
     conv2(cat[f, G]) = f @ W2[:, :C]^T + (G @ W2[:, C:]^T) broadcast over points, and the
     layer's `+ f_STE` (gcn3d.py:90 / :156) folded into the same pass (K5d) when given."""
     C = feature.shape[2]
-    G = ops.orl_global(feature, _geo_index32_exact(vertices, neighbor_num))  # (B,C)
     W2 = conv2_weight.squeeze(-1)
+    if (torch.is_autocast_enabled("cuda") and feature.is_cuda and C % 8 == 0 and feature.dtype == torch.float32
+            and _ORL_ONE_NODE):
+        # one autograd node: ORL + both 1x1 GEMMs + the residual pass; backward without fill / add passes
+        if ste_xyz_weight is not None:
+            return ops.orl_fuse(feature, _geo_index32_exact(vertices, neighbor_num), W2, None, vertices.float(),
+                                ste_xyz_weight.float())
+        return ops.orl_fuse(feature, _geo_index32_exact(vertices, neighbor_num), W2, f_STE)
+    G = ops.orl_global(feature, _geo_index32_exact(vertices, neighbor_num))  # (B,C)
     if torch.is_autocast_enabled("cuda") and feature.is_cuda and C % 8 == 0:
         W2f, W2g = ops.split_halves(W2, C)                                   # one cat in the backward
         lin = ops.linear_tc(feature, W2f)                                    # K6 (bf16 operands, fp32 accumulate)

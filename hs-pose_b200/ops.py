@@ -841,7 +841,7 @@ def gemm_splits(M, N, K):
 
 
 def gemm_bf16(a, b, a_mn=False, b_mn=False, bias=None, out=None, out_dtype=torch.bfloat16, splits=1,
-              stats=False, tile_n=0, ctas=0, bias_rows=None, rows_per_group=0, relu=False):
+              stats=False, tile_n=0, ctas=0, bias_rows=None, rows_per_group=0, relu=False, c_in=None):
     """K6: out[M,N] (+bias) = A . B^T on tcgen05 tensor cores (bf16 operands, fp32 accumulate).
 
     a: (M,K) [a_mn=False] or (K,M) [a_mn=True];  b: (N,K) [b_mn=False] or (K,N) [b_mn=True]; both bf16
@@ -871,9 +871,17 @@ def gemm_bf16(a, b, a_mn=False, b_mn=False, bias=None, out=None, out_dtype=torch
             bias_rows = _need(bias_rows, torch.float32, "bias_rows")
             if bias_rows.shape != ((M + rows_per_group - 1) // rows_per_group, N):
                 raise ValueError("gemm_bf16: bias_rows must be (ceil(M / rows_per_group), N)")
-        _call("hsp_gemm_bf16", _p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), M, N, K,
-              _p(bias), _p(bias_rows), int(rows_per_group), int(relu), _p(buf), ldo, int(f32), splits, _p(st),
-              tile_n, ctas, _stream())
+        if c_in is not None:      # residual: out = c_in + a . b^T (fp32 output only)
+            c_in = _need(c_in, torch.float32, "c_in")
+            if c_in.shape != (M, N) or not f32 or splits != 1:
+                raise ValueError("gemm_bf16: c_in must be (M, N) fp32 with an fp32, unsplit output")
+            _call("hsp_gemm_bf16_acc", _p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), M, N, K,
+                  _p(bias), _p(bias_rows), int(rows_per_group), int(relu), _p(c_in), c_in.stride(0), _p(buf), ldo,
+                  int(f32), splits, _p(st), tile_n, ctas, _stream())
+        else:
+            _call("hsp_gemm_bf16", _p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), M, N, K,
+                  _p(bias), _p(bias_rows), int(rows_per_group), int(relu), _p(buf), ldo, int(f32), splits, _p(st),
+                  tile_n, ctas, _stream())
     res = buf
     if splits > 1:
         res = buf[0] if splits == 1 else buf.sum(dim=0)
@@ -955,6 +963,84 @@ def linear_tc(x, W, b=None):
     shape = x.shape
     y = _LinearTC.apply(x.reshape(-1, shape[-1]), W, b)
     return y.view(*shape[:-1], W.shape[0])
+
+
+class _OrlFuse(torch.autograd.Function):
+    """The tail of every HS layer on the mixed-precision path as ONE autograd node:
+        out = feature + feature @ W2[:, :C]^T + (G @ W2[:, C:]^T)[:, None, :] + STE,   G = get_ORL_global(feature)
+    (reference gcn3d.py:109-113 / :183-187 and the `+ f_STE` of :90 / :156; K5a + two K6 GEMMs + K5d).  `feature`
+    feeds three consumers; as separate nodes autograd sums their three gradients with two full-size element-wise
+    passes over a zero-filled ORL buffer.  Here the pass-through gradient enters the dgrad GEMM as its residual
+    (hsp_gemm_bf16_acc) and the ORL backward adds its (order-independent) terms on top: no fill, no add pass."""
+
+    @staticmethod
+    def forward(ctx, feature, idx32, W2, ste, xyz, wxyz):
+        feature = _need(feature, torch.float32, "feature")
+        idx32 = _need(idx32, torch.int32, "idx")
+        B, N, C = feature.shape
+        k = idx32.shape[2]
+        need_grad = ctx.needs_input_grad[0]
+        lib = _lib.load()
+        W2b = _as_gemm_operand(W2)                                  # (C, 2C) bf16 (a view of the parameter shadow)
+        Wf, Wg = W2b[:, :C], W2b[:, C:]
+        sdt = F32
+        if ste is not None:
+            ste = _need(ste, ste.dtype if ste.dtype == torch.bfloat16 else torch.float32, "ste")
+            sdt = BF16 if ste.dtype == torch.bfloat16 else F32
+        if xyz is not None:
+            xyz = _need(xyz, torch.float32, "xyz")
+            wxyz = _need(wxyz, torch.float32, "wxyz")
+        with torch.cuda.device(feature.device):
+            ws = _workspace(lib.hsp_orl_global_workspace_bytes(B, N, C), feature.device)
+            G = torch.empty(B, C, dtype=torch.float32, device=feature.device)
+            am = torch.empty(B, N, C, dtype=torch.uint8, device=feature.device) if need_grad else None
+            _call("hsp_orl_global_fwd", _p(feature), _p(idx32), B, N, C, k, _p(G), _p(am), _p(ws), ws.numel(),
+                  _stream())
+            f16 = feature.view(B * N, C).to(torch.bfloat16)
+            G16 = G.to(torch.bfloat16)
+            lin = gemm_bf16(f16, Wf)                                 # (B*N, C) bf16
+            gproj = gemm_bf16(G16, Wg).float()                       # (B, C): bf16-rounded like linear_tc(...).float()
+            out = torch.empty_like(feature)
+            _call("hsp_residual_sum_fwd", _p(feature), _p(lin), BF16, _p(gproj), _p(ste), sdt, _p(xyz), _p(wxyz),
+                  B, N, C, _p(out), _stream())
+        ctx.save_for_backward(f16, G16, W2b, idx32, am, xyz)
+        ctx.meta = (B, N, C, k, None if ste is None else sdt)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        f16, G16, W2b, idx32, am, xyz = ctx.saved_tensors
+        B, N, C, k, sdt = ctx.meta
+        Wf, Wg = W2b[:, :C], W2b[:, C:]
+        g = _need(g.float(), torch.float32, "g")
+        want_w = xyz is not None and ctx.needs_input_grad[5]
+        with torch.cuda.device(g.device):
+            g16 = torch.empty(B, N, C, dtype=torch.bfloat16, device=g.device)
+            ggp = torch.empty(B, C, dtype=torch.float32, device=g.device)
+            gwp = torch.empty(B, C, 3, dtype=torch.float32, device=g.device) if want_w else None
+            _call("hsp_residual_sum_bwd", _p(g), _p(xyz) if want_w else None, B, N, C, _p(g16), _p(ggp), _p(gwp),
+                  _stream())
+            g16m = g16.view(B * N, C)
+            ggp16 = ggp.to(torch.bfloat16)
+            dfeat = None
+            if ctx.needs_input_grad[0]:
+                # d feature = g (pass-through) + g16 @ W2f (the GEMM's residual input) + ORL scatter (on top)
+                dfeat = gemm_bf16(g16m, Wf, b_mn=True, out_dtype=torch.float32, c_in=g.view(B * N, C))
+                dG = gemm_bf16(ggp16, Wg, b_mn=True, out_dtype=torch.float32)          # (B, C)
+                _call("hsp_orl_global_bwd", _p(dG), _p(idx32), _p(am), B, N, C, k, _p(dfeat), _stream())
+                dfeat = dfeat.view(B, N, C)
+            dW2 = None
+            if ctx.needs_input_grad[2]:
+                dW2 = torch.cat([_wgrad(g16m, f16), _wgrad(ggp16, G16)], dim=1)         # (C, 2C)
+        d_ste = None
+        if sdt is not None and ctx.needs_input_grad[3]:
+            d_ste = g16 if sdt == BF16 else g
+        return dfeat, None, dW2, d_ste, None, (gwp.sum(dim=0) if want_w else None)
+
+
+def orl_fuse(feature, idx32, W2, ste=None, xyz=None, wxyz=None):
+    """Fused ORL + residual (+ STE) tail of an HS layer (mixed-precision path; C % 8 == 0)."""
+    return _OrlFuse.apply(feature, idx32, W2, ste, xyz, wxyz)
 
 
 # ------------------------------------------------------------ K8: fused loss graph

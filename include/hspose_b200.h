@@ -288,6 +288,13 @@ int hsp_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb
                   int M, int N, int K, const float* bias, const float* bias_rows, int rows_per_group,
                   int relu, void* out, int ldo, int out_f32, int splits, float* stats, int tile_n,
                   int ctas, void* stream);
+/* Same, with a residual: out = c_in + A . B^T (+ biases), c_in (M, ldc) fp32 or NULL (fp32 output, splits == 1,
+ * N % 4 == 0, 16-byte aligned rows).  c_in may not alias out.  A dgrad GEMM whose result joins a gradient that
+ * already exists (the pass-through term of a residual connection) needs no separate element-wise add.        */
+int hsp_gemm_bf16_acc(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major,
+                      int M, int N, int K, const float* bias, const float* bias_rows, int rows_per_group,
+                      int relu, const float* c_in, int ldc, void* out, int ldo, int out_f32, int splits,
+                      float* stats, int tile_n, int ctas, void* stream);
 
 /* ------------------------------------------------------------------ K8 ---
  * The 19-term loss graph of training stage 'PoseNet_only' (L1 loss type), forward and backward:

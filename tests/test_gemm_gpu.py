@@ -147,3 +147,23 @@ def test_linear_bn_relu_node_matches_torch(cuda):
     assert rel(x.grad, xr.grad) < 2e-2 and rel(W.grad, Wr.grad) < 1e-2
     assert rel(b.grad, br.grad) < 1e-2 or br.grad.norm().item() < 1e-3      # db ~ 0 through BatchNorm
     assert rel(gamma.grad, gr.grad) < 1e-2 and rel(beta.grad, ber.grad) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K,b_mn", [(4112, 128, 128, True), (1028, 256, 256, True), (300, 512, 64, False),
+                                        (131584, 128, 128, True)])
+def test_gemm_residual_input(cuda, M, N, K, b_mn):
+    """hsp_gemm_bf16_acc: out = c_in + A . B^T in the epilogue (the pass-through gradient of a residual connection
+    joins the dgrad GEMM), ragged M, every tile width; c_in is not modified."""
+    import hspose_b200.ops as ops
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn(M, K, device=cuda, generator=g).to(torch.bfloat16)
+    B = (torch.randn(K, N, device=cuda, generator=g) if b_mn else torch.randn(N, K, device=cuda, generator=g)).to(torch.bfloat16)
+    C = torch.randn(M, N, device=cuda, generator=g) * 3
+    keep = C.clone()
+    ref = C + A.float() @ (B.float() if b_mn else B.float().t())
+    out = ops.gemm_bf16(A, B, b_mn=b_mn, out_dtype=torch.float32, c_in=C)
+    assert torch.equal(C, keep)
+    assert (out - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    plain = ops.gemm_bf16(A, B, b_mn=b_mn, out_dtype=torch.float32)
+    assert torch.equal(out, plain + C) or (out - (plain + C)).abs().max().item() <= 1e-6 * ref.abs().max().item()
+    assert torch.equal(out, ops.gemm_bf16(A, B, b_mn=b_mn, out_dtype=torch.float32, c_in=C))   # reproducible

@@ -733,3 +733,39 @@ def test_boundary_errors_index_range_and_xyz_grad(cuda):
         ops.surface_conv(v.clone().requires_grad_(), idx, dirn, 7, 16)
     ops.surface_conv(v, idx, dirn, 7, 16).sum().backward()        # the supported case still works
     assert dirn.grad is not None
+
+
+@pytest.mark.parametrize("B,N,C,k,surface", [(3, 1028, 128, 20, False), (2, 257, 256, 20, False), (2, 1028, 128, 20, True),
+                                             (2, 64, 512, 8, False)])
+def test_orl_fuse_one_node_matches_the_separate_nodes(cuda, B, N, C, k, surface):
+    """ops.orl_fuse (ORL + two 1x1 GEMMs + residual as one autograd node; the pass-through gradient is the dgrad
+    GEMM's residual input and the ORL backward adds on top) == the five separate nodes it replaces: same forward
+    bits, gradients equal up to the order of three fp32 additions."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(B * N + C)
+    xyz = (torch.randn(B, N, 3, generator=g) * 0.05).to(cuda)
+    idx = ops.knn3(xyz, xyz, k)[1]
+    feat0 = torch.randn(B, N, C, generator=g).to(cuda)
+    W0 = (torch.randn(C, 2 * C, generator=g) / (2 * C) ** 0.5).to(cuda)
+    ste0 = torch.randn(B, N, C, generator=g).to(cuda).to(torch.bfloat16)
+    wx0 = torch.randn(C, 3, generator=g).to(cuda)
+    gout = torch.randn(B, N, C, generator=g).to(cuda)
+    res = []
+    for fused in (True, False):
+        feat, W = feat0.clone().requires_grad_(), W0.clone().requires_grad_()
+        ste, wx = ste0.clone().requires_grad_(), wx0.clone().requires_grad_()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if fused:
+                out = ops.orl_fuse(feat, idx, W, None if surface else ste, xyz if surface else None, wx if surface else None)
+            else:
+                G = ops.orl_global(feat, idx)
+                Wf, Wg = ops.split_halves(W, C)
+                lin = ops.linear_tc(feat, Wf)
+                gproj = ops.linear_tc(G, Wg).float()
+                out = (ops.residual_sum(feat, lin, gproj, None, xyz, wx) if surface
+                       else ops.residual_sum(feat, lin, gproj, ste))
+        out.backward(gout)
+        res.append((out.detach(), feat.grad, W.grad, wx.grad if surface else ste.grad.float()))
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert (a - b).abs().max().item() <= 2e-6 * b.abs().max().item() + 1e-7
