@@ -108,3 +108,38 @@ def test_flat_parameter_adam_equals_per_tensor_adam():
         opt_b.step()
     for (n, pa), (_, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
         assert torch.allclose(pa, pb, atol=1e-7), n
+
+
+def test_flat_buffers_alignment_and_bf16_parameter_shadow():
+    """FlatGradients: every parameter starts on a 32-byte boundary of the flat fp32 buffers (= 16 bytes in the bf16
+    shadow: TMA descriptors of the tensor-core GEMMs need that), flatten_params keeps values and identities, and
+    the shadow refreshed by ONE cast serves any view of a parameter bit-for-bit like a per-tensor cast would."""
+    import torch
+    from hspose_b200 import ops, parallel
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv1d(5, 7, 1), torch.nn.BatchNorm1d(7), torch.nn.Linear(3, 11))
+    before = {n: p.detach().clone() for n, p in net.named_parameters()}
+    flat = parallel.FlatGradients(net.parameters())
+    assert all(off % 8 == 0 for off in flat.offsets)
+    flat.flatten_params()
+    for n, p in net.named_parameters():
+        assert torch.equal(p, before[n]) and p.data_ptr() % 32 == flat.flat_param.data_ptr() % 32
+    shadow = flat.refresh_shadow()
+    assert shadow.dtype == torch.bfloat16 and shadow.numel() == flat.flat_param.numel()
+    w = net[0].weight.squeeze(-1)[:, 1:4]                 # a strided view of a parameter
+    with ops.weight_shadow(flat.flat_param, shadow):
+        served = ops._as_gemm_operand(net[2].weight)      # contiguous (11, 3) -> padded copy (pitch not 16 B)
+        assert torch.equal(served.float(), net[2].weight.detach().to(torch.bfloat16).float())
+        off = (w.data_ptr() - flat.flat_param.data_ptr()) // 4
+        view = shadow.as_strided(w.shape, w.stride(), off)
+        assert torch.equal(view.float(), w.detach().to(torch.bfloat16).float())
+    assert ops._shadow is None                            # scoped: nothing leaks out of the step
+    with torch.no_grad():
+        net[2].weight.add_(1.0)
+    assert not torch.equal(shadow.as_strided(net[2].weight.shape, net[2].weight.stride(),
+                                             (net[2].weight.data_ptr() - flat.flat_param.data_ptr()) // 4).float(),
+                           net[2].weight.detach().to(torch.bfloat16).float())     # stale until refreshed ...
+    flat.refresh_shadow()
+    assert torch.equal(shadow.as_strided(net[2].weight.shape, net[2].weight.stride(),
+                                         (net[2].weight.data_ptr() - flat.flat_param.data_ptr()) // 4).float(),
+                       net[2].weight.detach().to(torch.bfloat16).float())         # ... which the engine does every step
