@@ -95,9 +95,14 @@ def test_posenet_eval_free_running_report(cuda, golden, capsys):
     diffs = {n: float(np.abs(out[n] - g[f"k20_{n}"]).max()) for n in NAMES}
     with capsys.disabled():
         print(f"\n[T3 free-running] RF-F neighbour-set flips {flips}/{rows}; max-abs diffs {diffs}")
-    assert flips / rows < 0.15   # flips cascade through the 4 RF-F layers; outputs bound below
-    for n in NAMES:   # reference self-noise floor is ~2e-3 (App. C.2)
-        assert diffs[n] < 1e-2, (n, diffs[n])
+    # Flips cascade through the 4 RF-F layers (the reference's own self-noise floor is ~2e-3 on the rotations when
+    # only its GEMM blocking changes).  Measured on the B200 (deterministic): 190 / 3212 rows = 5.9 %,
+    # p_green_R 2.6e-4, p_red_R 4.2e-4, f_* 1e-6 .. 5e-6, Pred_T 2.0e-5, Pred_s 2.1e-5.  Bars = 1.5x the flips and
+    # 3x the output differences, so a regression of the fp32 path shows up here.
+    assert flips / rows < 0.09
+    bars = {"p_green_R": 8e-4, "p_red_R": 1.3e-3, "f_green_R": 1.5e-5, "f_red_R": 1.5e-5, "Pred_T": 6e-5, "Pred_s": 6.5e-5}
+    for n in NAMES:
+        assert diffs[n] < bars[n], (n, diffs[n])
 
 
 def _train_module(cuda):
