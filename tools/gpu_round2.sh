@@ -17,6 +17,7 @@ timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --cloc
 wc -l gpurun_out/launches_$TAG.csv
 python tools/summarize_launches.py gpurun_out/launches_$TAG.csv 2 > gpurun_out/${TAG}_launches_summary.txt 2>/dev/null
 gzip -f -k gpurun_out/launches_$TAG.csv
+# NOTE: ~420 captures of the B = 128 step with --set full took 25 GPU-minutes in round 2: cap the count when the budget is short
 timeout 1500 ncu --profile-from-start off --set full --clock-control none --import-source on \
    -k regex:'gemm_tc|losses_|optim_|augment|split_bf16|knn|graph_conv|surface_conv|orl_|bn_|upsample|residual|gather_max|chamfer|kf_|dir_reduce|sqnorm|colmax|pair_dirs|absmax|normalize_cols' -c 420 -f -o gpurun_out/prof_$TAG python tools/ncu_step.py 128 bf16 > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_full_$TAG.log
