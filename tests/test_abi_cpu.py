@@ -109,3 +109,24 @@ def test_flags_proxy_follows_the_reference_namespace_when_present():
         assert hf.get_flags().train == 0 and hf.FLAGS.train == 0
     finally:
         hf.FLAGS.train = old
+
+
+def test_argument_validation_returns_einval_without_touching_a_gpu():
+    """Every entry point validates its arguments before any CUDA call: NULL pointers / bad sizes come back as
+    HSP_EINVAL on a box without a device (error behaviour of the boundary, checked on the round-2 entry points)."""
+    import ctypes
+    from hspose_b200 import _lib
+    lib = _lib.load()
+    einval = lib.hsp_depth_to_cloud(None, None, None, None, 0, 1, 8, 8, None, None, None)
+    assert einval != 0 and lib.hsp_strerror(einval)
+    assert lib.hsp_sample_points(None, None, None, ctypes.c_ulonglong(0), 1, 64, 16, None, None, None) == einval
+    assert lib.hsp_normalize_cols_fwd(None, 0, ctypes.c_float(1e-12), None, None, None) == einval
+    assert lib.hsp_normalize_cols_bwd(None, None, None, 0, ctypes.c_float(1e-12), None, None) == einval
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    # a residual needs an fp32, unsplit output and N % 4 == 0
+    assert lib.hsp_gemm_bf16_acc(p, 8, 0, p, 8, 0, 4, 6, 8, None, None, 0, 0, p, 8, p, 8, 1, 1, None, 0, 0, None) == einval
+    assert lib.hsp_gemm_bf16_acc(p, 8, 0, p, 8, 0, 4, 8, 8, None, None, 0, 0, p, 8, p, 8, 0, 1, None, 0, 0, None) == einval
+    assert lib.hsp_gather_max_bwd(None, None, None, None, 1, 8, 4, 2, 4, 4, None, None) == einval
+    assert lib.hsp_upsample_rows_bwd(None, None, 1, 4, 8, 8, 8, 0, 0, None, None) == einval
+    assert lib.hsp_chamfer_bwd(None, None, None, None, None, None, 1, 8, 8, None, None, None) == einval
